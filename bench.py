@@ -1,0 +1,475 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline measurement (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1], the QuantizeLinear up_proj operands):
+    x  bf16 [8192, 4096]   A8 per-token   SymQuantizer forward + STE backward
+    W  bf16 [11008, 4096]  W4 per-channel SymQuantizer forward + STE backward
+One step = those four launches (K1 x, K1 W, K3 x, K3 W).  Algorithmic bytes per
+step = 10 B/elem * (33,554,432 + 45,088,768) = 786.4 MB.
+
+Metric: "fake-quant fwd+bwd GB/s" = algorithmic bytes of all ranks / max-over-ranks
+device time.  Prints ONE JSON line (rank 0).  Extra objects on the same line:
+roofline (dominant kernel, live CUDA-event timing), cpu_baseline (torch-eager
+port of the reference on the host cores), e2e (host buffers through the C ABI's
+host entry points, H2D + D2H inside the timed region), qlinear (K4 tcgen05 GEMM),
+config1_fp32 (BASELINE configs[0] shapes), clocks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_TOK, K_IN, N_OUT = 8192, 4096, 11008
+A_BITS, W_BITS = 8, 4
+CLIP = (-2.0, 2.0)
+ELEMS = T_TOK * K_IN + N_OUT * K_IN
+BYTES_PER_ELEM_BF16 = 10  # fwd 2e + bwd 3e, e = 2
+STEP_BYTES = ELEMS * BYTES_PER_ELEM_BF16
+METRIC = "fake-quant fwd+bwd GB/s"
+WORKLOAD = ("configs[1]: QuantizeLinear up_proj operands, x bf16[8192,4096] A8 per-token + "
+            "W bf16[11008,4096] W4 per-channel, SymQuantizer fwd + STE bwd")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def make_inputs(seed: int):
+    """Synthetic configs[1] tensors on the CPU (SURVEY.md 8d config 2 distributions)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(T_TOK, K_IN, generator=g)
+    idx = torch.randint(0, x.numel(), (x.numel() // 1000,), generator=g)
+    x.view(-1)[idx] *= 20.0
+    w = torch.randn(N_OUT, K_IN, generator=g) * 0.02
+    gx = torch.randn(T_TOK, K_IN, generator=g)
+    gw = torch.randn(N_OUT, K_IN, generator=g)
+    return [t.bfloat16() for t in (x, w, gx, gw)]
+
+
+# ----------------------------------------------------------------------------
+# clocks sampler (pynvml; falls back to nvidia-smi)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._th = None
+        self._nv = None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+            return self
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                util = nv.nvmlDeviceGetUtilizationRates(self._h).gpu
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((mhz, util))
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def stop(self):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join(timeout=2)
+        loaded = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------
+class Step:
+    """One hot-path step on preallocated device buffers, launched through the C
+    ABI with raw pointers (what the Python boundary does, minus allocation)."""
+
+    def __init__(self, x, w, gx, gw):
+        from llm_qat_b200 import _lib
+
+        self.L = _lib.lib()
+        self.lib = _lib
+        self.x, self.w, self.gx, self.gw = x, w, gx, gw
+        self.yx, self.yw = torch.empty_like(x), torch.empty_like(w)
+        self.dx, self.dw = torch.empty_like(x), torch.empty_like(w)
+        self.names = ["sym_fwd_x_a8", "sym_fwd_w_w4", "ste_bwd_x", "ste_bwd_w"]
+        self.kernel_bytes = [x.numel() * 4, w.numel() * 4, x.numel() * 6, w.numel() * 6]
+
+    def launch(self, i, stream):
+        L, BF16 = self.L, 1
+        if i == 0:
+            rc = L.qat_sym_fwd(self.x.data_ptr(), self.yx.data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, T_TOK, K_IN, BF16,
+                               A_BITS, 0, 0, stream)
+        elif i == 1:
+            rc = L.qat_sym_fwd(self.w.data_ptr(), self.yw.data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, N_OUT, K_IN, BF16,
+                               W_BITS, 0, 0, stream)
+        elif i == 2:
+            rc = L.qat_ste_bwd(self.gx.data_ptr(), self.x.data_ptr(), self.dx.data_ptr(), 0, CLIP[0], CLIP[1],
+                               self.x.numel(), BF16, stream)
+        else:
+            rc = L.qat_ste_bwd(self.gw.data_ptr(), self.w.data_ptr(), self.dw.data_ptr(), 0, CLIP[0], CLIP[1],
+                               self.w.numel(), BF16, stream)
+        self.lib.check(rc, self.names[i])
+
+    def run(self, stream):
+        for i in range(4):
+            self.launch(i, stream)
+
+
+def time_config1_fp32(device, steps):
+    """BASELINE configs[0] shapes on the GPU: fp32 [8192,4096], fwd+bwd per quantizer."""
+    from llm_qat_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1234)
+    x = (torch.randn(8192, 4096, generator=g) * 0.5).to(device)
+    gr = torch.randn(8192, 4096, generator=g).to(device)
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name, fn, bits in (("sym_w4", L.qat_sym_fwd, 4), ("sym_a8", L.qat_sym_fwd, 8),
+                           ("asym_a8", L.qat_asym_fwd, 8), ("asym_a4", L.qat_asym_fwd, 4)):
+        def once():
+            _lib.check(fn(x.data_ptr(), y.data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, 8192, 4096, 0, bits, 0, 0, st))
+            _lib.check(L.qat_ste_bwd(gr.data_ptr(), x.data_ptr(), dx.data_ptr(), 0, -2.0, 2.0, x.numel(), 0, st))
+        for _ in range(3):
+            once()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            once()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_fwd_bwd": round(ms, 4), "GBps": round(x.numel() * 20 / ms / 1e6, 1)}
+    return out
+
+
+def time_qlinear(device, x, w, steps, pk):
+    """K4: integer-grid tcgen05 GEMM at configs[1]; codes produced by K1."""
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.utils_quant import fake_quant_forward, qlinear_i8
+
+    _, qw, _, ew, _ = fake_quant_forward(w, W_BITS, False, True, want_y=False, codes_kind=CODES_I8, want_scales=True)
+    _, qx, _, ex, _ = fake_quant_forward(x, A_BITS, False, True, want_y=False, codes_kind=CODES_I8, want_scales=True)
+
+    def gemm_only():
+        return qlinear_i8(qx, qw, ex, ew, torch.bfloat16)
+
+    def fwd():  # what QuantizeLinear.forward costs per call: quantize x, quantize W, GEMM
+        _, qx2, _, ex2, _ = fake_quant_forward(x, A_BITS, False, True, want_y=False, codes_kind=CODES_I8,
+                                               want_scales=True)
+        _, qw2, _, ew2, _ = fake_quant_forward(w, W_BITS, False, True, want_y=False, codes_kind=CODES_I8,
+                                               want_scales=True)
+        return qlinear_i8(qx2, qw2, ex2, ew2, torch.bfloat16)
+
+    res = {}
+    flop = 2.0 * T_TOK * K_IN * N_OUT
+    for name, fn in (("gemm", gemm_only), ("forward", fwd)):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[name] = {"ms": round(ms, 4), "TOPs": round(flop / ms / 1e9, 1), "tokens_per_s": round(T_TOK / ms * 1e3)}
+    res["roofline"] = {"bound": "tensor", "achieved": res["gemm"]["TOPs"], "peak": pk["bf16_tflops"],
+                       "unit": "TFLOP/s", "frac": round(res["gemm"]["TOPs"] / pk["bf16_tflops"], 4),
+                       "traffic": None,
+                       "note": "kind::i8 MMA (nominal 2x the bf16 rate) against the measured bf16 peak"}
+    return res
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; llm-qat_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    import llm_qat_b200
+    from llm_qat_b200 import _lib
+    from llm_qat_b200.host_api import fake_quant_fwd_bwd_host
+
+    _lib.check(_lib.lib().qat_check_device(), "device check")
+    pk = peaks()
+    hx, hw, hgx, hgw = make_inputs(1234 + rank)   # each rank: its own token batch (data parallel)
+    hx, hw, hgx, hgw = [t.pin_memory() for t in (hx, hw, hgx, hgw)]
+    x, w, gx, gw = [t.to(device, non_blocking=True) for t in (hx, hw, hgx, hgw)]
+    step = Step(x, w, gx, gw)
+    torch.cuda.synchronize()
+    K, W = args.steps, max(args.warmup, 3)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    sampler = ClockSampler(local).start()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- region 1: K steps, launched as a CUDA graph of one step (device-resident inputs)
+    for _ in range(W):
+        step.run(stream)
+    torch.cuda.synchronize()
+    graph, used_graph = None, False
+    try:
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap):
+                step.run(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for _ in range(W):
+            graph.replay()
+        used_graph = True
+    except Exception as e:  # capture unsupported: fall back to direct launches
+        print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing direct launches", file=sys.stderr)
+        graph = None
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        if graph is not None:
+            graph.replay()
+        else:
+            step.run(stream)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = (_lib.launch_count() - launches0) if graph is None else 4 * K
+    if dist is not None:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * STEP_BYTES / (ms_step * 1e-3) / 1e9
+
+    # ---- region 2: the same K steps with an event pair around every launch (roofline)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    torch.cuda.synchronize()
+    for k in range(K):
+        evs[k][0].record()
+        for i in range(4):
+            step.launch(i, stream)
+            evs[k][i + 1].record()
+    torch.cuda.synchronize()
+    per_kernel_ms = [statistics.mean(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) for i in range(4)]
+    dom = max(range(4), key=lambda i: per_kernel_ms[i])
+    achieved = step.kernel_bytes[dom] / (per_kernel_ms[dom] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": step.names[dom], "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
+        "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
+        "peak_source": pk["source"], "bytes_per_launch": step.kernel_bytes[dom],
+        "us_per_launch": round(per_kernel_ms[dom] * 1e3, 2),
+        "all_kernels": {n: {"us": round(ms * 1e3, 2), "GBps": round(b / ms / 1e6, 1),
+                            "frac": round(b / ms / 1e6 / pk["hbm_gbs"], 4)}
+                        for n, ms, b in zip(step.names, per_kernel_ms, step.kernel_bytes)},
+    }
+
+    # ---- e2e: host (pinned) buffers through the C ABI host entry points
+    Ke = max(3, min(K, 10))
+    yx = torch.empty_like(hx).pin_memory()
+    dxh = torch.empty_like(hx).pin_memory()
+    yw = torch.empty_like(hw).pin_memory()
+    dwh = torch.empty_like(hw).pin_memory()
+
+    def e2e_step():
+        fake_quant_fwd_bwd_host(hx, hgx, CLIP, A_BITS, symmetric=True, device=device, y=yx, gx=dxh)
+        fake_quant_fwd_bwd_host(hw, hgw, CLIP, W_BITS, symmetric=True, device=device, y=yw, gx=dwh)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(Ke):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": round(world * STEP_BYTES * Ke / (e2e_ms * 1e-3) / 1e9, 2), "unit": "GB/s",
+           "h2d_bytes_per_step": ELEMS * 2 * 2, "d2h_bytes_per_step": ELEMS * 2 * 2, "steps": Ke,
+           "ms_per_step": round(e2e_ms / Ke, 3), "wall_ms_per_step": round(wall_ms / Ke, 3),
+           "api": "llm_qat_b200.host_api.fake_quant_fwd_bwd_host -> qat_sym_fwd_bwd_host (pinned host buffers)"}
+
+    extras = {}
+    if rank == 0:
+        try:
+            extras["qlinear"] = time_qlinear(device, x, w, max(3, min(K, 20)), pk)
+        except Exception as e:
+            extras["qlinear"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            extras["config1_fp32"] = time_config1_fp32(device, max(3, min(K, 20)))
+        except Exception as e:
+            extras["config1_fp32"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_port(hx, hw, hgx, hgw, budget_s=12.0)
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": STEP_BYTES, "l2": "inputs larger than L2 "
+                   "(x+W = 157 MB per step, 786 MB touched between re-reads)",
+                   "parallelism": f"dp{world}: every rank fake-quantizes its own 8192-token batch and weight "
+                                  "replica; rows are independent, no data-path collective",
+                   "launch": "CUDA graph of one step, replayed K times" if used_graph else "direct launches"},
+        "gpu_launches": launches,
+        "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    line.update(extras)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# CPU port of the reference (cpu_baseline leg and --impl reference arm)
+# ----------------------------------------------------------------------------
+def run_cpu_port(hx, hw, hgx, hgw, budget_s: float, steps: int | None = None, warmup: int = 1):
+    """Times oracle/torch_chain.py (the torch-eager port of utils_quant.py) on
+    the host cores over the SAME workload; a step = fwd+bwd of x and of W."""
+    from oracle import torch_chain as tc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def step():
+        tc.fwd_bwd(hx, hgx, A_BITS, True, CLIP)
+        tc.fwd_bwd(hw, hgw, W_BITS, True, CLIP)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() - t_start > budget_s or len(times) >= 50:
+            break
+    best = min(times)
+    mean = statistics.mean(times)
+    return {"value": round(STEP_BYTES / mean / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"full configs[1] step (x + W fwd+bwd, {ELEMS} bf16 elements) x {len(times)} "
+                      f"repetitions, mean; best {STEP_BYTES / best / 1e9:.3f} GB/s",
+            "ms_per_step": round(mean * 1e3, 1), "threads": torch.get_num_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hx, hw, hgx, hgw = make_inputs(1234)
+    K, W = args.steps, max(args.warmup, 1)
+    K = min(K, 20)  # bounded: ~0.5 s per step on 8 cores
+    cb = run_cpu_port(hx, hw, hgx, hgw, budget_s=0.0, steps=K, warmup=min(W, 3))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))), "steps": K, "warmup": min(W, 3),
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": STEP_BYTES,
+                   "note": "reference's torch CPU path (oracle/torch_chain.py port; /root/reference cannot "
+                           "travel to the GPU box), all host threads, rank 0 only"},
+        "gpu_launches": 0,
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+/*
+ * qat_b200.h — C ABI of libqat_b200.so: hand-written sm_100a kernels for
+ * LLM-QAT's fake-quantization hot path.
+ *
+ * The reference (JingyangXiang/LLM-QAT) has no FFI: its hot path is eager
+ * PyTorch in models/utils_quant.py.  This header is the thin layer that a
+ * drop-in `models/utils_quant.py` binds with ctypes; each
+ * entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the
+ *     caller unless the name ends in `_host`;
+ *   - tensors are dense row-major `[rows, cols]`; one row == one reduction set
+ *     (per-token / per-output-channel / per-(b,h) / whole tensor — the caller
+ *     flattens exactly as utils_quant.py:50-70 does);
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on
+ *     it, the library never synchronises and never allocates;
+ *   - return value: 0 on success, a QAT_ERR_* or cudaError_t otherwise;
+ *     qat_last_error() returns a thread-local message;
+ *   - outputs must not alias inputs;
+ *   - arithmetic follows the reference's op order bit-for-bit (SURVEY.md
+ *     appendix A): no FMA contraction, IEEE division, round-half-even, and in
+ *     bf16 one rounding to bf16 after every op.
+ */
+#ifndef QAT_B200_H_
+#define QAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QAT_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* element types of x / y / g / gx */
+#define QAT_F32 0
+#define QAT_BF16 1
+
+/* optional integer-code output */
+#define QAT_CODES_NONE 0
+#define QAT_CODES_I8 1  /* saturating to [-127,127] (Sym) / [0,255] as uint8 (Asym); NaN -> 0.  GEMM feed. */
+#define QAT_CODES_I16 2 /* exact; NaN -> INT16_MIN.  What parity tests compare. */
+
+/* error codes (cudaError_t values are passed through unchanged, all < 1000) */
+#define QAT_OK 0
+#define QAT_ERR_BAD_ARG 1001
+#define QAT_ERR_UNSUPPORTED 1002
+#define QAT_ERR_WORKSPACE 1003
+#define QAT_ERR_NO_DEVICE 1004
+
+int qat_version(void);
+const char* qat_last_error(void);
+/* Number of kernels this library has launched in the calling process (all
+ * threads); bench.py reports the delta over its timed region. */
+uint64_t qat_launch_count(void);
+/* 0 when a CUDA device with compute capability 10.x is current, else an error. */
+int qat_check_device(void);
+
+/*
+ * Workspace (bytes) the forward entry points need for a [rows, cols] tensor.
+ * Rows that fit one CTA's registers (the per-token / per-channel case) need
+ * none; longer rows (layerwise mode: rows == 1, cols == numel) use a two-phase
+ * reduce-then-apply and need 16 bytes per row.
+ */
+size_t qat_fwd_workspace_bytes(int64_t rows, int64_t cols, int dtype);
+
+/*
+ * SymQuantizer.forward — utils_quant.py:37-74.
+ *   m = max|x_row|; s = fl(fl(1/fl(m+1e-6)) * Q), Q = 2^(bits-1)-1;
+ *   q = rint(fl(x*s)); y = fl(q / fl(s+1e-6)).
+ * y      [rows, cols] dtype, may be NULL (codes-only mode for the GEMM feed)
+ * codes  [rows, cols] int8 / int16 per `codes_kind`, may be NULL
+ * row_s  [rows] float (s), row_e [rows] float (the dequant divisor), may be NULL
+ * mask   packed STE mask, bit i%8 of byte i/8 = (lo < x_i < hi), may be NULL;
+ *        lo/hi are only read when mask != NULL (utils_quant.py:85-86).
+ */
+int qat_sym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row_s, float* row_e,
+                uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
+                int bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * AsymQuantizer.forward — utils_quant.py:96-149.
+ *   a = fl(fl(max-min)+1e-8); b = min; S = 2^bits-1;
+ *   q = rint(fl(fl(fl(x-b)/a)*S)); y = fl(fl(fl(q/S)*a)+b).
+ * codes: uint8 (QAT_CODES_I8, bits<=8) or int16; row_a / row_b [rows] float.
+ */
+int qat_asym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row_a, float* row_b,
+                 uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
+                 int bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * SymQuantizer.backward / AsymQuantizer.backward — utils_quant.py:77-87, 152-162.
+ *   gx_i = (x_i >= hi || x_i <= lo) ? 0 : g_i      (bounds compared in x's dtype)
+ * mask_out (optional) receives the packed pass-mask; n = number of elements.
+ */
+int qat_ste_bwd(const void* g, const void* x, void* gx, uint8_t* mask_out, float clip_lo,
+                float clip_hi, int64_t n, int dtype, void* stream);
+
+/* Same backward, driven by a forward-emitted packed mask instead of x
+ * (reads 2e + 1/8 bytes per element instead of 3e). */
+int qat_ste_bwd_from_mask(const void* g, const uint8_t* mask, void* gx, int64_t n, int dtype,
+                          void* stream);
+
+/*
+ * QuantizeLinear low-bit weight path — utils_quant.py:202-242 (w_bits in {1,2}).
+ * w_eff = fl(fl(q - w) + w) with q the 1-bit sign / 2-bit 4-level quantization
+ * scaled by the row (or tensor) mean |w|.  rows = out_features.
+ */
+size_t qat_lowbit_workspace_bytes(int64_t rows, int layerwise); /* 8 B per row, or 8 B layerwise */
+int qat_lowbit_weight_fwd(const void* w, void* w_eff, int64_t rows, int64_t cols, int dtype,
+                          int w_bits, int layerwise, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/*
+ * QuantizeLinear.forward contraction — utils_quant.py:250 on integer-grid
+ * operands:  out[t, n] = (sum_k qx[t,k] * qw[n,k]) / (ex[t] * ew[n]).
+ * tcgen05 (kind::i8, s32 accumulators in TMEM), TMA-fed, dual-scale epilogue.
+ *   qx [T, K] int8, qw [N, K] int8 (both K-major), ex [T], ew [N] float,
+ *   out [T, N] in `out_dtype`.  K % 16 == 0 required (TMA row pitch).
+ */
+int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const float* ex, const float* ew,
+                       void* out, int64_t T, int64_t N, int64_t K, int out_dtype, void* stream);
+
+/* Host-buffer convenience entry points (pinned or pageable host memory):
+ * copy in, run, copy out on `stream`; `dev_scratch` must hold
+ * qat_host_scratch_bytes(...) bytes of device memory. */
+size_t qat_host_scratch_bytes(int64_t rows, int64_t cols, int dtype, int with_backward);
+int qat_sym_fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_host,
+                         float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
+                         int bits, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+int qat_asym_fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_host,
+                          float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
+                          int bits, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAT_B200_H_ */

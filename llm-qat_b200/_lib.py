@@ -1,0 +1,86 @@
+"""ctypes binding of libqat_b200.so (the C ABI declared in include/qat_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is
+missing, or a kernel call fails, this raises.  ``check(rc)`` turns a non-zero
+return code into ``RuntimeError`` with the library's thread-local message.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libqat_b200.so")
+
+QAT_F32, QAT_BF16 = 0, 1
+CODES_NONE, CODES_I8, CODES_I16 = 0, 1, 2
+ERR_UNSUPPORTED = 1002
+
+_lib = None
+
+
+def _declare(lib):
+    P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+    sig = {
+        "qat_version": (I, []),
+        "qat_last_error": (c_char_p, []),
+        "qat_launch_count": (c_uint64, []),
+        "qat_check_device": (I, []),
+        "qat_fwd_workspace_bytes": (Z, [L, L, I]),
+        # x, y, codes, codes_kind, st0, st1, mask, lo, hi, rows, cols, dtype, bits, ws, ws_bytes, stream
+        "qat_sym_fwd": (I, [P, P, P, I, P, P, P, F, F, L, L, I, I, P, Z, P]),
+        "qat_asym_fwd": (I, [P, P, P, I, P, P, P, F, F, L, L, I, I, P, Z, P]),
+        # g, x, gx, mask_out, lo, hi, n, dtype, stream
+        "qat_ste_bwd": (I, [P, P, P, P, F, F, L, I, P]),
+        # g, mask, gx, n, dtype, stream
+        "qat_ste_bwd_from_mask": (I, [P, P, P, L, I, P]),
+        "qat_lowbit_workspace_bytes": (Z, [L, I]),
+        # w, w_eff, rows, cols, dtype, w_bits, layerwise, ws, ws_bytes, stream
+        "qat_lowbit_weight_fwd": (I, [P, P, L, L, I, I, I, P, Z, P]),
+        # qx, qw, ex, ew, out, T, N, K, out_dtype, stream
+        "qat_qlinear_i8_fwd": (I, [P, P, P, P, P, L, L, L, I, P]),
+        "qat_host_scratch_bytes": (Z, [L, L, I, I]),
+        # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
+        "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),
+        "qat_asym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+def lib():
+    """The loaded library; raises ImportError with build instructions if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing. Build it with `python llm-qat_b200/build.py` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "llm-qat_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    """Names the header declares and the binding expects (used by the CPU tests)."""
+    return list(_declare(lib()).keys())
+
+
+def last_error() -> str:
+    msg = lib().qat_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str = "libqat_b200") -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib().qat_launch_count())

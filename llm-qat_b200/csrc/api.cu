@@ -1,0 +1,74 @@
+// api.cu — library bookkeeping: version, thread-local error text, launch
+// counter, device check.  No kernels here.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace qat {
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (int)e;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int num_sms() {
+  // cached per device ordinal; 148 on B200
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      cached_sms = sms;
+    cached_dev = dev;
+  }
+  return cached_sms;
+}
+}  // namespace qat
+
+extern "C" {
+
+int qat_version(void) { return QAT_B200_VERSION; }
+
+const char* qat_last_error(void) { return qat::g_err; }
+
+uint64_t qat_launch_count(void) { return qat::g_launches.load(std::memory_order_relaxed); }
+
+int qat_check_device(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    qat::set_error("no CUDA device visible (%s); libqat_b200 has no CPU fallback",
+                   e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return QAT_ERR_NO_DEVICE;
+  }
+  int dev = 0, major = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return qat::cuda_fail(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return qat::cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10) {
+    qat::set_error("device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+    return QAT_ERR_NO_DEVICE;
+  }
+  return QAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,622 @@
+// fakequant.cu — K1 (Sym), K2 (Asym) and K5 (long-row / layerwise) forward
+// kernels of the fake-quantization hot path, hand-written for sm_100a.
+//
+// Replaces the eager ATen chains of /root/reference/models/utils_quant.py:50-72
+// (9 kernels, ~18 tensor passes) and :110-147 (3 reductions + 9 elementwise)
+// with ONE pass: each row is read from HBM exactly once with 128-bit streaming
+// loads, held in registers across the abs-max / min-max warp-shuffle tree, then
+// quantized, dequantized and written back with 128-bit streaming stores.
+// Optional side outputs (integer codes for the tcgen05 GEMM, row scales, packed
+// STE mask) come out of the same pass.
+//
+// HBM-bound: algorithmic traffic = 2*sizeof(T) bytes per element (+1/8 B with
+// the mask, +1 or 2 B with codes).  See DESIGN.md section "K1/K2".
+#include "common.cuh"
+
+namespace qat {
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct FwdParams {
+  const void* x;
+  void* y;
+  void* codes;
+  int codes_kind;
+  float* st0;  // Sym: s      Asym: a (= alpha + 1e-8)
+  float* st1;  // Sym: e      Asym: beta
+  uint8_t* mask;
+  float lo, hi;  // already rounded to the tensor dtype by the host wrapper
+  int64_t rows;
+  int64_t cols;
+  int64_t nvec;  // vectors (VEC) or elements (scalar path) per row
+  float qmax;    // Sym: Q = 2^(bits-1)-1     Asym: S = 2^bits-1
+  int group;     // threads cooperating on one row (power of two, >= 32)
+  // long-row path
+  uint32_t* ws;
+  int64_t chunk;  // vectors per CTA
+};
+
+// ---- reductions --------------------------------------------------------------
+__device__ __forceinline__ void warp_reduce(RowStat& r, bool sym) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (sym) {
+      r.amax_bits = max(r.amax_bits, __shfl_xor_sync(kFull, r.amax_bits, o));
+    } else {
+      r.mx = fmaxf(r.mx, __shfl_xor_sync(kFull, r.mx, o));
+      r.mn = fminf(r.mn, __shfl_xor_sync(kFull, r.mn, o));
+      r.nan |= __shfl_xor_sync(kFull, r.nan, o);
+    }
+  }
+}
+
+__device__ __forceinline__ RowStat stat_identity() {
+  RowStat r;
+  r.amax_bits = 0u;
+  r.mx = -INFINITY;
+  r.mn = INFINITY;
+  r.nan = 0u;
+  return r;
+}
+
+// Reduce over `group` consecutive threads of the CTA (group % 32 == 0); every
+// thread of the group receives the result.  One __syncthreads when group > 32.
+template <bool SYM>
+__device__ __forceinline__ void group_reduce(RowStat& r, int group, uint32_t* sm_u, float* sm_mx,
+                                             float* sm_mn) {
+  warp_reduce(r, SYM);
+  if (group > 32) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+      if (SYM) {
+        sm_u[warp] = r.amax_bits;
+      } else {
+        sm_mx[warp] = r.mx;
+        sm_mn[warp] = r.mn;
+        sm_u[warp] = r.nan;
+      }
+    }
+    __syncthreads();
+    const int nw = group >> 5;
+    const int base = (warp / nw) * nw;
+    RowStat t = stat_identity();
+    if (lane < nw) {
+      if (SYM) {
+        t.amax_bits = sm_u[base + lane];
+      } else {
+        t.mx = sm_mx[base + lane];
+        t.mn = sm_mn[base + lane];
+        t.nan = sm_u[base + lane];
+      }
+    }
+    warp_reduce(t, SYM);
+    r = t;
+  }
+}
+
+template <int DT, bool SYM>
+__device__ __forceinline__ void accumulate_vec(RowStat& r, const uint4& v) {
+  if (SYM) {
+    if (DT == QAT_F32) {
+      r.amax_bits = max(r.amax_bits, v.x & 0x7fffffffu);
+      r.amax_bits = max(r.amax_bits, v.y & 0x7fffffffu);
+      r.amax_bits = max(r.amax_bits, v.z & 0x7fffffffu);
+      r.amax_bits = max(r.amax_bits, v.w & 0x7fffffffu);
+    } else {
+      // packed |bf16| maxima; r.amax_bits holds two u16 lanes until finalised
+      r.amax_bits = __vmaxu2(r.amax_bits, v.x & 0x7fff7fffu);
+      r.amax_bits = __vmaxu2(r.amax_bits, v.y & 0x7fff7fffu);
+      r.amax_bits = __vmaxu2(r.amax_bits, v.z & 0x7fff7fffu);
+      r.amax_bits = __vmaxu2(r.amax_bits, v.w & 0x7fff7fffu);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < Num<DT>::kPerVec; ++i) {
+      float f = vec_get<DT>(v, i);
+      r.mx = fmaxf(r.mx, f);
+      r.mn = fminf(r.mn, f);
+      r.nan |= (f != f) ? 1u : 0u;
+    }
+  }
+}
+
+template <int DT, bool SYM>
+__device__ __forceinline__ void accumulate_scalar(RowStat& r, float f) {
+  if (SYM) {
+    r.amax_bits = max(r.amax_bits, __float_as_uint(f) & 0x7fffffffu);
+  } else {
+    r.mx = fmaxf(r.mx, f);
+    r.mn = fminf(r.mn, f);
+    r.nan |= (f != f) ? 1u : 0u;
+  }
+}
+
+// bf16 Sym keeps two u16 lanes while accumulating; fold them into fp32 |x| bits
+template <int DT, bool SYM, bool VEC>
+__device__ __forceinline__ void finalize_thread_stat(RowStat& r) {
+  if (SYM && VEC && DT == QAT_BF16) {
+    uint32_t m = max(r.amax_bits & 0xffffu, r.amax_bits >> 16);
+    r.amax_bits = m << 16;
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ float load_scalar(const void* x, int64_t i) {
+  if (DT == QAT_F32) return reinterpret_cast<const float*>(x)[i];
+  return bf16lo(reinterpret_cast<const uint16_t*>(x)[i]);
+}
+
+// ---- per-vector quantize + all outputs ------------------------------------
+// `e0` = flat element index of the vector's first element.
+template <int DT, bool SYM, typename Scale>
+__device__ __forceinline__ void emit_vec(const FwdParams& p, const Scale& sc, const uint4& v,
+                                         int64_t e0, bool valid) {
+  constexpr int N = Num<DT>::kPerVec;
+  float yv[N], qv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) yv[i] = sc.apply(vec_get<DT>(v, i), &qv[i]);
+  if (p.y != nullptr && valid) {
+    uint4 o;
+    if (DT == QAT_F32) {
+      o.x = __float_as_uint(yv[0]);
+      o.y = __float_as_uint(yv[1]);
+      o.z = __float_as_uint(yv[2]);
+      o.w = __float_as_uint(yv[3]);
+    } else {
+      o.x = pack_bf16x2(yv[0], yv[1]);
+      o.y = pack_bf16x2(yv[2 % N], yv[3 % N]);
+      o.z = pack_bf16x2(yv[4 % N], yv[5 % N]);
+      o.w = pack_bf16x2(yv[6 % N], yv[7 % N]);
+    }
+    stg_stream(reinterpret_cast<char*>(p.y) + e0 * Num<DT>::kBytes, o);
+  }
+  if (p.codes != nullptr && valid) {
+    if (p.codes_kind == QAT_CODES_I8) {
+      uint32_t w[N / 4];
+#pragma unroll
+      for (int i = 0; i < N / 4; ++i)
+        w[i] = (uint32_t)code_i8<SYM>(qv[4 * i]) | ((uint32_t)code_i8<SYM>(qv[4 * i + 1]) << 8) |
+               ((uint32_t)code_i8<SYM>(qv[4 * i + 2]) << 16) |
+               ((uint32_t)code_i8<SYM>(qv[4 * i + 3]) << 24);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(p.codes) + e0;
+      if (N == 4) {
+        *reinterpret_cast<uint32_t*>(dst) = w[0];
+      } else {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[(N / 4) - 1]);
+      }
+    } else {
+      uint32_t w[N / 2];
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i)
+        w[i] = (uint32_t)(uint16_t)code_i16(qv[2 * i]) |
+               ((uint32_t)(uint16_t)code_i16(qv[2 * i + 1]) << 16);
+      int16_t* dst = reinterpret_cast<int16_t*>(p.codes) + e0;
+      if (N == 4) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2 % (N / 2)], w[3 % (N / 2)]);
+      }
+    }
+  }
+  if (p.mask != nullptr) {  // uniform branch; host guarantees (rows*cols) byte alignment rules
+    uint32_t pass = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float xf = vec_get<DT>(v, i);
+      pass |= ((xf >= p.hi || xf <= p.lo) ? 0u : 1u) << i;  // utils_quant.py:85-86
+    }
+    if (N == 8) {
+      if (valid) p.mask[e0 >> 3] = (uint8_t)pass;
+    } else {
+      // two adjacent lanes hold the two nibbles of one byte
+      uint32_t mine = valid ? pass : 0u;
+      uint32_t other = __shfl_xor_sync(kFull, mine, 1);
+      if (valid && !(threadIdx.x & 1)) p.mask[e0 >> 3] = (uint8_t)(mine | (other << 4));
+    }
+  }
+}
+
+template <int DT, bool SYM, typename Scale>
+__device__ __forceinline__ void emit_scalar(const FwdParams& p, const Scale& sc, float xf,
+                                            int64_t e0) {
+  float q;
+  float yf = sc.apply(xf, &q);
+  if (p.y != nullptr) {
+    if (DT == QAT_F32)
+      reinterpret_cast<float*>(p.y)[e0] = yf;
+    else
+      reinterpret_cast<__nv_bfloat16*>(p.y)[e0] = __float2bfloat16_rn(yf);
+  }
+  if (p.codes != nullptr) {
+    if (p.codes_kind == QAT_CODES_I8)
+      reinterpret_cast<uint8_t*>(p.codes)[e0] = code_i8<SYM>(q);
+    else
+      reinterpret_cast<int16_t*>(p.codes)[e0] = code_i16(q);
+  }
+}
+
+template <int DT, bool SYM>
+struct ScaleOf;
+template <int DT>
+struct ScaleOf<DT, true> {
+  using type = SymScale<DT>;
+  static __device__ __forceinline__ type make(const RowStat& r, float qmax) {
+    type s;
+    s.derive(__uint_as_float(r.amax_bits), qmax);
+    return s;
+  }
+  static __device__ __forceinline__ float st0(const type& s) { return s.s; }
+  static __device__ __forceinline__ float st1(const type& s) { return s.e; }
+};
+template <int DT>
+struct ScaleOf<DT, false> {
+  using type = AsymScale<DT>;
+  static __device__ __forceinline__ type make(const RowStat& r, float qmax) {
+    type s;
+    s.derive(r.mx, r.mn, r.nan != 0u, qmax);
+    return s;
+  }
+  static __device__ __forceinline__ float st0(const type& s) { return s.a; }
+  static __device__ __forceinline__ float st1(const type& s) { return s.beta; }
+};
+
+// =============================================================================
+// K1 / K2: one row per thread group, the row lives in registers between the
+// reduction and the quantize pass => exactly one HBM read + one HBM write.
+//   grid  = ceil(rows / (blockDim / group)),  block = max(group, 256)
+//   ITERS = 16-byte vectors (or scalars) per thread, compile-time unrolled so
+//           all loads of a row are in flight before the first use.
+// =============================================================================
+template <int DT, int ITERS, bool SYM, bool VEC>
+__global__ void __launch_bounds__(1024) rowquant_kernel(const FwdParams p) {
+  __shared__ uint32_t sm_u[32];
+  __shared__ float sm_mx[32], sm_mn[32];
+
+  const int group = p.group;
+  const int t = threadIdx.x & (group - 1);
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x / group) + (threadIdx.x / group);
+  const bool row_ok = row < p.rows;
+  const int64_t row_e0 = row * p.cols;
+
+  RowStat st = stat_identity();
+  using SO = ScaleOf<DT, SYM>;
+
+  if (VEC) {
+    uint4 v[ITERS];
+    const char* xrow = reinterpret_cast<const char*>(p.x) + row_e0 * Num<DT>::kBytes;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int64_t j = t + (int64_t)i * group;
+      if (row_ok && j < p.nvec) {
+        v[i] = ldg_stream(xrow + j * 16);
+      } else {
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int64_t j = t + (int64_t)i * group;
+      if (SYM || (row_ok && j < p.nvec)) accumulate_vec<DT, SYM>(st, v[i]);  // zeros are neutral for |x|
+    }
+    finalize_thread_stat<DT, SYM, VEC>(st);
+    group_reduce<SYM>(st, group, sm_u, sm_mx, sm_mn);
+    const typename SO::type sc = SO::make(st, p.qmax);
+    if (t == 0 && row_ok) {
+      if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
+      if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int64_t j = t + (int64_t)i * group;
+      const bool valid = row_ok && j < p.nvec;
+      emit_vec<DT, SYM>(p, sc, v[i], row_e0 + j * Num<DT>::kPerVec, valid);
+    }
+  } else {
+    float v[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int64_t j = t + (int64_t)i * group;
+      v[i] = (row_ok && j < p.nvec) ? load_scalar<DT>(p.x, row_e0 + j) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int64_t j = t + (int64_t)i * group;
+      if (row_ok && j < p.nvec) accumulate_scalar<DT, SYM>(st, v[i]);
+    }
+    group_reduce<SYM>(st, group, sm_u, sm_mx, sm_mn);
+    const typename SO::type sc = SO::make(st, p.qmax);
+    if (t == 0 && row_ok) {
+      if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
+      if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int64_t j = t + (int64_t)i * group;
+      if (row_ok && j < p.nvec) emit_scalar<DT, SYM>(p, sc, v[i], row_e0 + j);
+    }
+  }
+}
+
+// =============================================================================
+// K5: rows too long for one CTA's registers (layerwise mode: the whole tensor
+// is one row).  Phase 1 reduces chunks and merges with atomics on an ordered
+// key; phase 2 re-reads (L2-resident up to ~100 MB) and applies.
+//   ws[4*row + 0] = Sym |x| max bits / Asym ordered-key max
+//   ws[4*row + 1] = Asym ordered-key min     ws[4*row + 2] = Asym NaN flag
+// =============================================================================
+__global__ void ws_init_kernel(uint32_t* ws, int64_t rows) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) {
+    ws[4 * r + 0] = 0u;
+    ws[4 * r + 1] = 0xffffffffu;
+    ws[4 * r + 2] = 0u;
+    ws[4 * r + 3] = 0u;
+  }
+}
+
+template <int DT, bool SYM, bool VEC>
+__global__ void __launch_bounds__(256) longrow_stats_kernel(const FwdParams p) {
+  __shared__ uint32_t sm_u[32];
+  __shared__ float sm_mx[32], sm_mn[32];
+  const int64_t row = blockIdx.y;
+  const int64_t row_e0 = row * p.cols;
+  const int64_t j0 = (int64_t)blockIdx.x * p.chunk;
+  const int64_t j1 = min(j0 + p.chunk, p.nvec);
+  RowStat st = stat_identity();
+  if (VEC) {
+    const char* xrow = reinterpret_cast<const char*>(p.x) + row_e0 * Num<DT>::kBytes;
+    int64_t j = j0 + threadIdx.x;
+    for (; j + 3 * 256 < j1; j += 4 * 256) {
+      uint4 a = ldg_stream(xrow + j * 16);
+      uint4 b = ldg_stream(xrow + (j + 256) * 16);
+      uint4 c = ldg_stream(xrow + (j + 512) * 16);
+      uint4 d = ldg_stream(xrow + (j + 768) * 16);
+      accumulate_vec<DT, SYM>(st, a);
+      accumulate_vec<DT, SYM>(st, b);
+      accumulate_vec<DT, SYM>(st, c);
+      accumulate_vec<DT, SYM>(st, d);
+    }
+    for (; j < j1; j += 256) {
+      uint4 a = ldg_stream(xrow + j * 16);
+      accumulate_vec<DT, SYM>(st, a);
+    }
+  } else {
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += 256)
+      accumulate_scalar<DT, SYM>(st, load_scalar<DT>(p.x, row_e0 + j));
+  }
+  finalize_thread_stat<DT, SYM, VEC>(st);
+  group_reduce<SYM>(st, 256, sm_u, sm_mx, sm_mn);
+  if (threadIdx.x == 0) {
+    uint32_t* w = p.ws + 4 * row;
+    if (SYM) {
+      atomicMax(w, st.amax_bits);
+    } else {
+      if (st.mx >= st.mn) {  // at least one non-NaN value seen
+        atomicMax(w, ordered_key(st.mx));
+        atomicMin(w + 1, ordered_key(st.mn));
+      }
+      if (st.nan) atomicOr(w + 2, 1u);
+    }
+  }
+}
+
+template <int DT, bool SYM, bool VEC>
+__global__ void __launch_bounds__(256) longrow_apply_kernel(const FwdParams p) {
+  const int64_t row = blockIdx.y;
+  const int64_t row_e0 = row * p.cols;
+  const int64_t j0 = (int64_t)blockIdx.x * p.chunk;
+  const int64_t j1 = min(j0 + p.chunk, p.nvec);
+  const uint32_t* w = p.ws + 4 * row;
+  RowStat st;
+  st.amax_bits = w[0];
+  st.mx = SYM ? 0.f : ordered_unkey(w[0]);
+  st.mn = SYM ? 0.f : ordered_unkey(w[1]);
+  st.nan = w[2];
+  using SO = ScaleOf<DT, SYM>;
+  const typename SO::type sc = SO::make(st, p.qmax);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
+    if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
+  }
+  if (VEC) {
+    const char* xrow = reinterpret_cast<const char*>(p.x) + row_e0 * Num<DT>::kBytes;
+    // whole-CTA trip count so the mask shuffle inside emit_vec stays convergent
+    for (int64_t jb = j0; jb < j1; jb += 256) {
+      const int64_t j = jb + threadIdx.x;
+      const bool valid = j < j1;
+      uint4 v = valid ? ldg_stream(xrow + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+      emit_vec<DT, SYM>(p, sc, v, row_e0 + j * Num<DT>::kPerVec, valid);
+    }
+  } else {
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += 256)
+      emit_scalar<DT, SYM>(p, sc, load_scalar<DT>(p.x, row_e0 + j), row_e0 + j);
+  }
+}
+
+// ---- host-side dispatch -----------------------------------------------------
+constexpr int kMaxIters = 8;
+constexpr int kMaxGroup = 1024;
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct Plan {
+  bool vec;
+  bool fused;  // row fits registers
+  int64_t nvec;
+  int group, iters, block;
+  int64_t chunk, chunks;
+};
+
+Plan make_plan(const void* x, const void* y, int64_t rows, int64_t cols, int dtype) {
+  Plan pl{};
+  const int esz = dtype == QAT_F32 ? 4 : 2;
+  const int per = 16 / esz;
+  pl.vec = (cols % per == 0) && aligned16(x) && (y == nullptr || aligned16(y));
+  pl.nvec = pl.vec ? cols / per : cols;
+  // smallest power-of-two group (>=32) that keeps <= 4 vectors per thread,
+  // falling back to up to 8 per thread at the 1024-thread cap.
+  int group = 32;
+  while (group < kMaxGroup && (pl.nvec + group - 1) / group > 4) group <<= 1;
+  int64_t iters = (pl.nvec + group - 1) / group;
+  pl.fused = iters <= kMaxIters;
+  pl.group = group;
+  pl.iters = iters <= 2 ? 2 : iters <= 4 ? 4 : 8;
+  pl.block = group < 256 ? 256 : group;
+  if (!pl.fused) {
+    int64_t chunk = (pl.nvec + 4095) / 4096;
+    if (chunk < 2048) chunk = 2048;
+    chunk = (chunk + 255) / 256 * 256;  // multiple of the CTA width (keeps lane parity for the mask)
+    pl.chunk = chunk;
+    pl.chunks = (pl.nvec + chunk - 1) / chunk;
+  }
+  return pl;
+}
+
+template <int DT, bool SYM, bool VEC>
+int launch_fused(const FwdParams& p, const Plan& pl, cudaStream_t st) {
+  const int rows_per_cta = pl.block / pl.group;
+  const int64_t grid = (p.rows + rows_per_cta - 1) / rows_per_cta;
+  if (grid > 0x7fffffffLL) {
+    set_error("too many rows (%lld)", (long long)p.rows);
+    return QAT_ERR_UNSUPPORTED;
+  }
+  switch (pl.iters) {
+    case 2:
+      rowquant_kernel<DT, 2, SYM, VEC><<<(unsigned)grid, pl.block, 0, st>>>(p);
+      break;
+    case 4:
+      rowquant_kernel<DT, 4, SYM, VEC><<<(unsigned)grid, pl.block, 0, st>>>(p);
+      break;
+    default:
+      rowquant_kernel<DT, 8, SYM, VEC><<<(unsigned)grid, pl.block, 0, st>>>(p);
+      break;
+  }
+  QAT_CHECK_LAUNCH("rowquant_kernel");
+  return QAT_OK;
+}
+
+template <int DT, bool SYM, bool VEC>
+int launch_longrow(const FwdParams& p, const Plan& pl, cudaStream_t st) {
+  if (p.rows > 65535) {
+    set_error("long-row path supports at most 65535 rows (got %lld)", (long long)p.rows);
+    return QAT_ERR_UNSUPPORTED;
+  }
+  ws_init_kernel<<<(unsigned)((p.rows + 255) / 256), 256, 0, st>>>(p.ws, p.rows);
+  QAT_CHECK_LAUNCH("ws_init_kernel");
+  dim3 grid((unsigned)pl.chunks, (unsigned)p.rows);
+  longrow_stats_kernel<DT, SYM, VEC><<<grid, 256, 0, st>>>(p);
+  QAT_CHECK_LAUNCH("longrow_stats_kernel");
+  longrow_apply_kernel<DT, SYM, VEC><<<grid, 256, 0, st>>>(p);
+  QAT_CHECK_LAUNCH("longrow_apply_kernel");
+  return QAT_OK;
+}
+
+template <int DT, bool SYM>
+int dispatch(const FwdParams& p, const Plan& pl, cudaStream_t st) {
+  if (pl.fused)
+    return pl.vec ? launch_fused<DT, SYM, true>(p, pl, st) : launch_fused<DT, SYM, false>(p, pl, st);
+  return pl.vec ? launch_longrow<DT, SYM, true>(p, pl, st) : launch_longrow<DT, SYM, false>(p, pl, st);
+}
+
+float round_to_dtype(float v, int dtype) {
+  if (dtype == QAT_F32) return v;
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+template <bool SYM>
+int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, float* st1,
+              uint8_t* mask, float lo, float hi, int64_t rows, int64_t cols, int dtype, int bits,
+              void* workspace, size_t workspace_bytes, void* stream) {
+  QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16, "dtype must be QAT_F32 or QAT_BF16 (got %d)", dtype);
+  QAT_CHECK_ARG(rows >= 0 && cols >= 0, "negative shape [%lld, %lld]", (long long)rows, (long long)cols);
+  QAT_CHECK_ARG(SYM ? (bits >= 2 && bits <= 16) : (bits >= 1 && bits <= 15),
+                "unsupported num_bits %d", bits);
+  if (rows == 0 || cols == 0) return QAT_OK;
+  QAT_CHECK_ARG(x != nullptr, "x is NULL");
+  QAT_CHECK_ARG(y != nullptr || codes != nullptr || st0 != nullptr || st1 != nullptr || mask != nullptr,
+                "no output requested");
+  QAT_CHECK_ARG(codes == nullptr || codes_kind == QAT_CODES_I8 || codes_kind == QAT_CODES_I16,
+                "codes_kind must be QAT_CODES_I8 or QAT_CODES_I16 when codes != NULL");
+  QAT_CHECK_ARG(!(codes != nullptr && codes_kind == QAT_CODES_I8 && bits > 8),
+                "int8 codes need num_bits <= 8 (got %d)", bits);
+  QAT_CHECK_ARG(x != y, "y must not alias x");
+
+  Plan pl = make_plan(x, y, rows, cols, dtype);
+  if (codes != nullptr && pl.vec) {
+    // code stores are vectorised with the same element grouping
+    const int per = dtype == QAT_F32 ? 4 : 8;
+    const uintptr_t need = (uintptr_t)(codes_kind == QAT_CODES_I8 ? per : 2 * per);
+    QAT_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & (need - 1)) == 0, "codes pointer misaligned");
+  }
+  if (mask != nullptr) {
+    if (!pl.vec || (cols % 8 != 0 && rows != 1)) {
+      set_error("packed-mask output needs 16-byte aligned rows with cols %% 8 == 0 (cols=%lld)",
+                (long long)cols);
+      return QAT_ERR_UNSUPPORTED;
+    }
+    if (dtype == QAT_F32 && (cols % 8 != 0)) {
+      set_error("packed-mask output needs cols %% 8 == 0 for fp32 (cols=%lld)", (long long)cols);
+      return QAT_ERR_UNSUPPORTED;
+    }
+  }
+  FwdParams p{};
+  p.x = x;
+  p.y = y;
+  p.codes = codes;
+  p.codes_kind = codes_kind;
+  p.st0 = st0;
+  p.st1 = st1;
+  p.mask = mask;
+  p.lo = round_to_dtype(lo, dtype);
+  p.hi = round_to_dtype(hi, dtype);
+  p.rows = rows;
+  p.cols = cols;
+  p.nvec = pl.nvec;
+  p.qmax = SYM ? (float)((1 << (bits - 1)) - 1) : (float)((1 << bits) - 1);
+  p.group = pl.group;
+  p.ws = reinterpret_cast<uint32_t*>(workspace);
+  p.chunk = pl.chunk;
+  if (!pl.fused) {
+    const size_t need = (size_t)rows * 16;
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("row length %lld needs %zu bytes of workspace (got %zu)", (long long)cols, need,
+                workspace_bytes);
+      return QAT_ERR_WORKSPACE;
+    }
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == QAT_F32) return dispatch<QAT_F32, SYM>(p, pl, st);
+  return dispatch<QAT_BF16, SYM>(p, pl, st);
+}
+
+}  // namespace
+}  // namespace qat
+
+extern "C" {
+
+size_t qat_fwd_workspace_bytes(int64_t rows, int64_t cols, int dtype) {
+  if (rows <= 0 || cols <= 0) return 0;
+  // worst case (scalar path): one element per thread-iteration
+  (void)dtype;
+  // the scalar path may be chosen at run time when a pointer is misaligned, so
+  // size for it: fused iff cols <= kMaxGroup * kMaxIters elements.
+  if (cols <= (int64_t)qat::kMaxGroup * qat::kMaxIters) return 0;
+  return (size_t)rows * 16;
+}
+
+int qat_sym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row_s, float* row_e,
+                uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
+                int bits, void* workspace, size_t workspace_bytes, void* stream) {
+  return qat::fwd_entry<true>(x, y, codes, codes_kind, row_s, row_e, mask, clip_lo, clip_hi, rows,
+                              cols, dtype, bits, workspace, workspace_bytes, stream);
+}
+
+int qat_asym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row_a, float* row_b,
+                 uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
+                 int bits, void* workspace, size_t workspace_bytes, void* stream) {
+  return qat::fwd_entry<false>(x, y, codes, codes_kind, row_a, row_b, mask, clip_lo, clip_hi, rows,
+                               cols, dtype, bits, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+"""Drop-in replacement for the reference's ``models/utils_quant.py``.
+
+Same three public names, same signatures, no new parameters or buffers:
+
+* ``SymQuantizer.apply(input, clip_val, num_bits, layerwise)``   (reference utils_quant.py:31-87)
+* ``AsymQuantizer.apply(input, clip_val, num_bits, layerwise)``  (reference utils_quant.py:90-162)
+* ``QuantizeLinear(in, out, symmetric=True, bias=False, w_bits=32, a_bits=32,
+  act_layerwise=False, weight_layerwise=False)``                 (reference utils_quant.py:165-254)
+
+Every tensor op of the reference's eager chains runs here as one hand-written
+sm_100a kernel reached through the C ABI in ``include/qat_b200.h``.  Inputs must
+be CUDA tensors (fp32 or bf16): there is no CPU fallback.
+
+Install under the reference's import name before its model file is imported::
+
+    import llm_qat_b200; llm_qat_b200.install()      # sys.modules["models.utils_quant"] = this module
+    from models.modeling_llama_quant import LlamaForCausalLM
+
+Run-time knobs (environment; signatures stay the reference's):
+  QAT_B200_FUSED_LINEAR=0|1   QuantizeLinear uses the integer-grid tcgen05 GEMM (default 0 for now; 1
+                              when shapes/dtypes allow) or fake-quant kernels + F.linear.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import CODES_I8, CODES_I16, CODES_NONE, QAT_BF16, QAT_F32, check
+
+__all__ = ["SymQuantizer", "AsymQuantizer", "QuantizeLinear"]
+
+_DTYPES = {torch.float32: QAT_F32, torch.bfloat16: QAT_BF16}
+
+
+# ------------------------------------------------------------------ helpers
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"llm-qat_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}") from None
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: expected a CUDA tensor, got device {t.device}. "
+            "llm-qat_b200 runs only on B200 (sm_100a); there is no CPU fallback.")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _clip_bounds(clip_val):
+    """(lo, hi) as python floats.  The reference reads clip_val[0]/[1] as 0-dim
+    tensors in backward (utils_quant.py:85-86); a CPU clip tensor (the only kind
+    the model creates, :198,245) costs no device sync."""
+    if isinstance(clip_val, torch.Tensor):
+        lo, hi = clip_val.detach().reshape(-1)[:2].tolist()
+        return float(lo), float(hi)
+    lo, hi = clip_val
+    return float(lo), float(hi)
+
+
+def _reduction_view(input: torch.Tensor, layerwise: bool):
+    """(rows, cols) with one row per reduction set — utils_quant.py:50-70."""
+    if layerwise:
+        return 1, input.numel()
+    nd = input.dim()
+    if nd <= 3:
+        cols = input.shape[-1] if nd >= 1 else 1
+        return (input.numel() // cols if cols else 0), cols
+    if nd == 4:
+        # the reference does input.view(d0, d1, -1): raise like it does when not viewable
+        input.view(input.shape[0], input.shape[1], -1)
+        return input.shape[0] * input.shape[1], input.shape[2] * input.shape[3]
+    raise ValueError
+
+
+def fake_quant_forward(input: torch.Tensor, num_bits: int, layerwise: bool, symmetric: bool, *,
+                       want_y: bool = True, codes_kind: int = CODES_NONE, want_scales: bool = False,
+                       mask_clip=None):
+    """One launch of K1/K2 (or the two-phase K5 for long rows).
+
+    Returns ``(y, codes, st0, st1, mask)``; entries not requested are ``None``.
+    Sym: st0 = s, st1 = e (dequant divisor).  Asym: st0 = alpha + 1e-8, st1 = beta.
+    """
+    _require_cuda(input, "fake-quant forward")
+    dt = _dtype_code(input)
+    rows, cols = _reduction_view(input, layerwise)
+    if input.numel() == 0:
+        raise RuntimeError("fake-quant of an empty tensor (the reference's max() raises too)")
+    x = input.detach()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    dev = x.device
+    y = torch.empty_like(x) if want_y else None
+    codes = None
+    if codes_kind == CODES_I8:
+        codes = torch.empty(x.shape, dtype=torch.int8 if symmetric else torch.uint8, device=dev)
+    elif codes_kind == CODES_I16:
+        codes = torch.empty(x.shape, dtype=torch.int16, device=dev)
+    st0 = torch.empty(rows, dtype=torch.float32, device=dev) if want_scales else None
+    st1 = torch.empty(rows, dtype=torch.float32, device=dev) if want_scales else None
+    mask = None
+    lo = hi = 0.0
+    if mask_clip is not None:
+        lo, hi = mask_clip
+        mask = torch.empty((x.numel() + 7) // 8, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.qat_fwd_workspace_bytes(rows, cols, dt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    fn = L.qat_sym_fwd if symmetric else L.qat_asym_fwd
+    with torch.cuda.device(dev):
+        rc = fn(x.data_ptr(), _ptr(y), _ptr(codes), codes_kind, _ptr(st0), _ptr(st1), _ptr(mask),
+                lo, hi, rows, cols, dt, int(num_bits), _ptr(ws), ws_bytes, _stream_ptr(dev))
+    check(rc, "qat_sym_fwd" if symmetric else "qat_asym_fwd")
+    return y, codes, st0, st1, mask
+
+
+def ste_backward(grad_output: torch.Tensor, input: torch.Tensor, clip_val, *, want_mask: bool = False):
+    """K3: gx = g where clip[0] < x < clip[1] else 0 — utils_quant.py:83-87."""
+    _require_cuda(grad_output, "STE backward")
+    _require_cuda(input, "STE backward")
+    if grad_output.dtype != input.dtype:
+        raise TypeError(f"STE backward: grad dtype {grad_output.dtype} != input dtype {input.dtype}")
+    if grad_output.shape != input.shape:
+        raise RuntimeError(f"STE backward: grad shape {tuple(grad_output.shape)} != input shape {tuple(input.shape)}")
+    dt = _dtype_code(input)
+    lo, hi = _clip_bounds(clip_val)
+    g = grad_output if grad_output.is_contiguous() else grad_output.contiguous()
+    x = input.detach()
+    x = x if x.is_contiguous() else x.contiguous()
+    gx = torch.empty_like(g)
+    n = g.numel()
+    if n == 0:
+        return (gx, None) if want_mask else gx
+    mask = torch.empty((n + 7) // 8, dtype=torch.uint8, device=g.device) if want_mask else None
+    with torch.cuda.device(g.device):
+        rc = _lib.lib().qat_ste_bwd(g.data_ptr(), x.data_ptr(), gx.data_ptr(), _ptr(mask), lo, hi, n, dt,
+                                    _stream_ptr(g.device))
+    check(rc, "qat_ste_bwd")
+    return (gx, mask) if want_mask else gx
+
+
+def ste_backward_from_mask(grad_output: torch.Tensor, mask: torch.Tensor):
+    """K3 driven by a forward-emitted packed mask (reads 1/8 B/elem instead of x)."""
+    _require_cuda(grad_output, "STE backward")
+    dt = _dtype_code(grad_output)
+    g = grad_output if grad_output.is_contiguous() else grad_output.contiguous()
+    gx = torch.empty_like(g)
+    if g.numel() == 0:
+        return gx
+    with torch.cuda.device(g.device):
+        rc = _lib.lib().qat_ste_bwd_from_mask(g.data_ptr(), mask.data_ptr(), gx.data_ptr(), g.numel(), dt,
+                                              _stream_ptr(g.device))
+    check(rc, "qat_ste_bwd_from_mask")
+    return gx
+
+
+# ------------------------------------------------------------------ quantizers
+class SymQuantizer(torch.autograd.Function):
+    """Symmetric abs-max fake-quant with STE backward (reference utils_quant.py:31-87)."""
+
+    @staticmethod
+    def forward(ctx, input, clip_val, num_bits, layerwise):
+        ctx.save_for_backward(input, clip_val)
+        y, *_ = fake_quant_forward(input, num_bits, layerwise, symmetric=True)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, clip_val = ctx.saved_tensors
+        return ste_backward(grad_output, input, clip_val), None, None, None
+
+
+class AsymQuantizer(torch.autograd.Function):
+    """Min-max asymmetric fake-quant with STE backward (reference utils_quant.py:90-162)."""
+
+    @staticmethod
+    def forward(ctx, input, clip_val, num_bits, layerwise):
+        ctx.save_for_backward(input, clip_val)
+        y, *_ = fake_quant_forward(input, num_bits, layerwise, symmetric=False)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, clip_val = ctx.saved_tensors
+        return ste_backward(grad_output, input, clip_val), None, None, None
+
+
+class _LowBitWeight(torch.autograd.Function):
+    """w_bits in {1, 2}: forward value (q - w) + w, identity gradient
+    (reference utils_quant.py:202-242)."""
+
+    @staticmethod
+    def forward(ctx, weight, w_bits, layerwise):
+        _require_cuda(weight, "low-bit weight quant")
+        dt = _dtype_code(weight)
+        w = weight.detach()
+        w = w if w.is_contiguous() else w.contiguous()
+        out = torch.empty_like(w)
+        rows, cols = w.shape
+        L = _lib.lib()
+        ws_bytes = int(L.qat_lowbit_workspace_bytes(rows, int(bool(layerwise))))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
+        with torch.cuda.device(w.device):
+            rc = L.qat_lowbit_weight_fwd(w.data_ptr(), out.data_ptr(), rows, cols, dt, int(w_bits),
+                                         int(bool(layerwise)), _ptr(ws), ws_bytes, _stream_ptr(w.device))
+        check(rc, "qat_lowbit_weight_fwd")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None, None
+
+
+# ------------------------------------------------------------------ fused linear
+def _fused_linear_enabled() -> bool:
+    return os.environ.get("QAT_B200_FUSED_LINEAR", "0") == "1"
+
+
+class _QuantLinearFn(torch.autograd.Function):
+    """QuantizeLinear main path (3 <= w_bits <= 8, 3 <= a_bits <= 8, symmetric,
+    per-row scales) on the integer grid — reference utils_quant.py:197-201,244-250.
+
+    forward : K1 codes-only passes (int8 codes + row divisors + packed STE masks)
+              -> tcgen05 int8 GEMM with the dual-scale epilogue (K4).
+    backward: dequantized operands are rebuilt from codes (q / e, bit-identical
+              to the reference's fake-quant outputs); dgrad/wgrad are plain
+              library GEMMs; the STE masks saved by the forward gate them.
+    Saves 1 B/elem of codes + 1/8 B/elem of mask instead of the reference's two
+    dequantized tensors plus two unquantized inputs.
+    """
+
+    @staticmethod
+    def forward(ctx, input, weight, w_bits, a_bits):
+        lead = input.shape[:-1]
+        K = input.shape[-1]
+        N = weight.shape[0]
+        x2 = input.reshape(-1, K)
+        clip = (-2.0, 2.0)  # utils_quant.py:198,245
+        _, qx, _, ex, mx = fake_quant_forward(x2, a_bits, False, True, want_y=False, codes_kind=CODES_I8,
+                                              want_scales=True, mask_clip=clip)
+        _, qw, _, ew, mw = fake_quant_forward(weight, w_bits, False, True, want_y=False, codes_kind=CODES_I8,
+                                              want_scales=True, mask_clip=clip)
+        out = qlinear_i8(qx, qw, ex, ew, input.dtype)
+        ctx.save_for_backward(qx, qw, ex, ew, mx, mw)
+        ctx.in_shape = input.shape
+        ctx.dtype = input.dtype
+        return out.reshape(*lead, N)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        qx, qw, ex, ew, mx, mw = ctx.saved_tensors
+        g2 = grad_output.reshape(-1, grad_output.shape[-1])
+        g2 = g2 if g2.is_contiguous() else g2.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            wq = (qw.to(torch.float32) / ew[:, None]).to(ctx.dtype)      # == reference's fake-quant W
+            gx = ste_backward_from_mask(g2 @ wq, mx).reshape(ctx.in_shape)
+        if ctx.needs_input_grad[1]:
+            xq = (qx.to(torch.float32) / ex[:, None]).to(ctx.dtype)      # == reference's fake-quant x
+            gw = ste_backward_from_mask(g2.t() @ xq, mw)
+        return gx, gw, None, None
+
+
+def qlinear_i8(qx, qw, ex, ew, out_dtype):
+    """K4: out[t, n] = (sum_k qx[t,k] qw[n,k]) / (ex[t] * ew[n]) on tcgen05 (kind::i8)."""
+    T, K = qx.shape
+    N = qw.shape[0]
+    out = torch.empty((T, N), dtype=out_dtype, device=qx.device)
+    with torch.cuda.device(qx.device):
+        rc = _lib.lib().qat_qlinear_i8_fwd(qx.data_ptr(), qw.data_ptr(), ex.data_ptr(), ew.data_ptr(),
+                                           out.data_ptr(), T, N, K, _DTYPES[out_dtype], _stream_ptr(qx.device))
+    check(rc, "qat_qlinear_i8_fwd")
+    return out
+
+
+# ------------------------------------------------------------------ QuantizeLinear
+class QuantizeLinear(nn.Linear):
+    """nn.Linear whose weight and input are fake-quantized on every forward
+    (reference utils_quant.py:165-254).  State dict == {"weight"}; bias is
+    always None (the reference ignores the ``bias`` kwarg, :176)."""
+
+    def __init__(
+        self,
+        *kargs,
+        symmetric=True,
+        bias=False,
+        w_bits=32,
+        a_bits=32,
+        act_layerwise=False,
+        weight_layerwise=False,
+    ):
+        super(QuantizeLinear, self).__init__(*kargs, bias=False)
+        self.w_bits = w_bits
+        self.a_bits = a_bits
+        self.act_layerwise = act_layerwise
+        self.weight_layerwise = weight_layerwise
+        if self.a_bits < 32 and self.a_bits > 2:
+            self.act_quantizer = SymQuantizer if symmetric else AsymQuantizer
+
+    def _can_fuse(self, input_: torch.Tensor) -> bool:
+        return (
+            _fused_linear_enabled()
+            and 3 <= self.w_bits <= 8
+            and 3 <= self.a_bits <= 8
+            and getattr(self, "act_quantizer", None) is SymQuantizer
+            and not self.act_layerwise
+            and not self.weight_layerwise
+            and input_.is_cuda
+            and input_.dtype in _DTYPES
+            and input_.dtype == self.weight.dtype
+            and 1 <= input_.dim() <= 3
+            and input_.shape[-1] % 16 == 0
+            and input_.numel() > 0
+        )
+
+    def forward(self, input_):
+        assert len(self.weight.size()) == 2
+        real_weights = self.weight
+
+        if self._can_fuse(input_):
+            return _QuantLinearFn.apply(input_, real_weights, self.w_bits, self.a_bits)
+
+        if self.w_bits >= 32:
+            weight = self.weight
+        elif self.w_bits >= 3:
+            weight_clip_val = torch.tensor([-2.0, 2.0])
+            weight = SymQuantizer.apply(real_weights, weight_clip_val, self.w_bits, self.weight_layerwise)
+        else:
+            weight = _LowBitWeight.apply(real_weights, self.w_bits, self.weight_layerwise)
+        if self.a_bits < 32 and self.a_bits > 2:
+            act_clip_val = torch.tensor([-2.0, 2.0])
+            input_ = self.act_quantizer.apply(input_, act_clip_val, self.a_bits, self.act_layerwise)
+
+        out = nn.functional.linear(input_, weight)
+        if self.bias is not None:
+            out += self.bias.view(1, -1).expand_as(out)
+        return out

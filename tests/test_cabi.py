@@ -1,0 +1,125 @@
+"""CPU: the C-ABI library loads, exports every symbol include/qat_b200.h
+declares, and the Python boundary mirrors the reference's interface.  No
+kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "qat_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qat_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = header_functions()
+    for must in ("qat_sym_fwd", "qat_asym_fwd", "qat_ste_bwd", "qat_ste_bwd_from_mask", "qat_qlinear_i8_fwd",
+                 "qat_lowbit_weight_fwd", "qat_version", "qat_last_error", "qat_sym_fwd_bwd_host"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    import llm_qat_b200
+
+    path = llm_qat_b200._lib.LIB_PATH
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} declared in qat_b200.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (qat_[a-z0-9_]+)", out))
+    assert exported == set(header_functions()), exported ^ set(header_functions())
+
+
+def test_binding_covers_the_header():
+    import llm_qat_b200
+
+    assert sorted(llm_qat_b200._lib.exported_symbols()) == header_functions()
+    assert llm_qat_b200._lib.lib().qat_version() == 100
+
+
+def test_library_is_sm100a_native():
+    """SASS carries the Blackwell-only mnemonics: tcgen05 MMA, TMEM load, TMA."""
+    import llm_qat_b200
+
+    sass = subprocess.run(["cuobjdump", "-sass", llm_qat_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    import llm_qat_b200
+
+    L = llm_qat_b200._lib.lib()
+    # dtype 7 is invalid; pointers are never dereferenced on this path
+    rc = L.qat_sym_fwd(16, 32, 0, 0, 0, 0, 0, -2.0, 2.0, 4, 4, 7, 4, 0, 0, 0)
+    assert rc == 1001 and "dtype" in llm_qat_b200._lib.last_error()
+    rc = L.qat_sym_fwd(16, 32, 0, 0, 0, 0, 0, -2.0, 2.0, 4, 4, 0, 1, 0, 0, 0)
+    assert rc == 1001 and "num_bits" in llm_qat_b200._lib.last_error()
+    rc = L.qat_qlinear_i8_fwd(16, 16, 16, 16, 16, 8, 8, 12, 1, 0)
+    assert rc == 1001 and "multiple of 16" in llm_qat_b200._lib.last_error()
+    assert L.qat_fwd_workspace_bytes(8192, 4096, 0) == 0
+    assert L.qat_fwd_workspace_bytes(1, 1 << 25, 0) == 16
+    assert L.qat_host_scratch_bytes(8, 16, 1, 1) == 4 * 256
+
+
+def test_no_cpu_fallback():
+    from llm_qat_b200 import AsymQuantizer, QuantizeLinear, SymQuantizer
+
+    x = torch.randn(4, 8)
+    clip = torch.tensor([-2.0, 2.0])
+    for q in (SymQuantizer, AsymQuantizer):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            q.apply(x, clip, 4, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        QuantizeLinear(8, 4, w_bits=4, a_bits=8)(x)
+
+
+def test_quantize_linear_mirrors_reference_interface():
+    from llm_qat_b200 import AsymQuantizer, QuantizeLinear, SymQuantizer
+
+    lin = QuantizeLinear(16, 8, bias=True, w_bits=4, a_bits=8, act_layerwise=False, weight_layerwise=False)
+    assert isinstance(lin, torch.nn.Linear)
+    assert lin.bias is None                       # reference ignores bias= (utils_quant.py:176)
+    assert list(lin.state_dict().keys()) == ["weight"] and lin.weight.shape == (8, 16)
+    assert (lin.w_bits, lin.a_bits, lin.act_layerwise, lin.weight_layerwise) == (4, 8, False, False)
+    assert lin.act_quantizer is SymQuantizer
+    assert QuantizeLinear(16, 8, symmetric=False, a_bits=8).act_quantizer is AsymQuantizer
+    assert not hasattr(QuantizeLinear(16, 8, a_bits=32), "act_quantizer")   # :184
+    assert not hasattr(QuantizeLinear(16, 8, a_bits=2), "act_quantizer")
+    assert len(list(lin.buffers())) == 0 and len(list(lin.parameters())) == 1
+
+
+def test_install_aliases_reference_module_name():
+    import sys
+
+    import llm_qat_b200
+
+    llm_qat_b200.install("qat_test_models.utils_quant")
+    mod = sys.modules["qat_test_models.utils_quant"]
+    assert mod.QuantizeLinear is llm_qat_b200.QuantizeLinear and mod.SymQuantizer is llm_qat_b200.SymQuantizer
+    del sys.modules["qat_test_models.utils_quant"]
+
+
+def test_reduction_view_matches_reference_rules():
+    from llm_qat_b200.utils_quant import _reduction_view
+
+    assert _reduction_view(torch.zeros(6, 8), False) == (6, 8)
+    assert _reduction_view(torch.zeros(2, 3, 8), False) == (6, 8)
+    assert _reduction_view(torch.zeros(8), False) == (1, 8)
+    assert _reduction_view(torch.zeros(()), False) == (1, 1)
+    assert _reduction_view(torch.zeros(2, 3, 4, 8), False) == (6, 32)
+    assert _reduction_view(torch.zeros(2, 3, 4, 8), True) == (1, 192)
+    with pytest.raises(ValueError):
+        _reduction_view(torch.zeros(1, 1, 1, 1, 1), False)      # utils_quant.py:69-70
+    with pytest.raises(RuntimeError):                           # non-viewable 4-D raises like .view()
+        _reduction_view(torch.zeros(2, 3, 4, 8).transpose(1, 2), False)

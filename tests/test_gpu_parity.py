@@ -1,0 +1,318 @@
+"""GPU (-m gpu): the CUDA path, called through the reference-shaped Python
+boundary over the C ABI, against (i) the golden vectors generated from the live
+reference and (ii) the oracle on seeded inputs, bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+import qat_testutil as U
+from oracle import quant_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+CLIP = torch.tensor([-2.0, 2.0])
+
+
+def _q(name):
+    from llm_qat_b200 import AsymQuantizer, SymQuantizer
+
+    return SymQuantizer if name == "sym" else AsymQuantizer
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available(), "these tests need a B200"
+    import llm_qat_b200
+
+    assert llm_qat_b200._lib.lib().qat_check_device() == 0, llm_qat_b200._lib.last_error()
+    yield
+    torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_forward_bit_exact_vs_reference_goldens(dtype):
+    g = U.golden(dtype)
+    bad = []
+    for q, key, bits, lw in U.quant_cases(g):
+        x = U.bits_to_tensor(g[f"in/{key}"], dtype, "cuda")
+        y = _q(q).apply(x, CLIP, bits, lw)
+        assert y.shape == x.shape and y.dtype == x.dtype and y.is_contiguous()
+        ref = g[f"y/{q}/{key}/b{bits}/{'lw' if lw else 'row'}"]
+        nm = U.mismatches(U.tensor_bits(y), ref, dtype)
+        if nm:
+            bad.append((q, key, bits, lw, nm, ref.size))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_backward_bit_exact_vs_reference_goldens(dtype):
+    g = U.golden(dtype)
+    bad = []
+    for q, key, lw, lo, hi, gk in U.clip_cases(g):
+        x = U.bits_to_tensor(g[f"in/{key}"], dtype, "cuda").requires_grad_(True)
+        gr = U.bits_to_tensor(g[f"grad/{key}"], dtype, "cuda")
+        bits = 2 if q == "sym" else 3
+        y = _q(q).apply(x, torch.tensor([lo, hi]), bits, lw)
+        y.backward(gr)
+        nm = U.mismatches(U.tensor_bits(x.grad), g[gk], dtype)
+        if nm:
+            bad.append((gk, nm))
+    assert not bad, bad
+
+
+# --------------------------------------------------------------- codes, scales, masks vs oracle
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("sym", [True, False])
+def test_codes_scales_and_mask_bit_exact_vs_oracle(dtype, sym):
+    from llm_qat_b200._lib import CODES_I8, CODES_I16
+    from llm_qat_b200.utils_quant import fake_quant_forward
+
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(96, 1024, generator=gen) * 0.7)
+    x[3] = 0.0
+    x[5, 7] = 2.0
+    x[5, 8] = -2.0
+    x[7, ::5] = 3.0
+    x = x.to(U.DTYPES[dtype])
+    xn = U.tensor_to_f32(x)
+    for bits in (4, 8):
+        y, c16, st0, st1, mask = fake_quant_forward(x.cuda(), bits, False, sym, codes_kind=CODES_I16,
+                                                    want_scales=True, mask_clip=(-2.0, 2.0))
+        o = (qo.sym_forward if sym else qo.asym_forward)(xn, bits, False, dtype)
+        assert qo.count_mismatch(U.tensor_to_f32(y), o["y"]) == 0
+        np.testing.assert_array_equal(c16.cpu().numpy(), o["codes"].astype(np.int16))
+        if sym:
+            assert U.f32_mismatches(st0.cpu().numpy(), o["s"]) == 0
+            assert U.f32_mismatches(st1.cpu().numpy(), o["e"]) == 0
+        else:
+            assert U.f32_mismatches(st0.cpu().numpy(), o["a"]) == 0
+            assert U.f32_mismatches(st1.cpu().numpy(), o["beta"]) == 0
+        ob = qo.ste_backward(np.ones_like(xn), xn, -2.0, 2.0, dtype)
+        np.testing.assert_array_equal(mask.cpu().numpy(), qo.pack_mask(ob["mask"]))
+        # int8 GEMM feed: exact wherever the code fits, saturated otherwise
+        _, c8, _, _, _ = fake_quant_forward(x.cuda(), bits, False, sym, want_y=False, codes_kind=CODES_I8)
+        lo8, hi8 = (-127, 127) if sym else (0, 255)
+        np.testing.assert_array_equal(c8.cpu().numpy().astype(np.int32),
+                                      np.clip(o["codes"], lo8, hi8).astype(np.int32))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_backward_mask_variants_agree(dtype):
+    from llm_qat_b200.utils_quant import fake_quant_forward, ste_backward, ste_backward_from_mask
+
+    gen = torch.Generator().manual_seed(11)
+    for shape in [(64, 4096), (33, 1000), (1, 8), (5, 12)]:
+        x = (torch.randn(*shape, generator=gen) * 1.5).to(U.DTYPES[dtype]).cuda()
+        g = torch.randn(*shape, generator=gen).to(U.DTYPES[dtype]).cuda()
+        gx, mask = ste_backward(g, x, CLIP, want_mask=True)
+        ob = qo.ste_backward(U.tensor_to_f32(g), U.tensor_to_f32(x), -2.0, 2.0, dtype)
+        assert qo.count_mismatch(U.tensor_to_f32(gx), ob["gx"]) == 0
+        np.testing.assert_array_equal(mask.cpu().numpy(), qo.pack_mask(ob["mask"]))
+        gx2 = ste_backward_from_mask(g, mask)
+        assert torch.equal(gx.view(torch.int16 if dtype == "bf16" else torch.int32),
+                           gx2.view(torch.int16 if dtype == "bf16" else torch.int32))
+        if shape[1] % 8 == 0:
+            _, _, _, _, fmask = fake_quant_forward(x, 4, False, True, mask_clip=(-2.0, 2.0))
+            assert torch.equal(fmask, mask)
+
+
+# --------------------------------------------------------------- shapes / modes at scale vs oracle
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,lw", [
+    ((512, 4096), False),        # activations: per token
+    ((256, 11008), False),       # down_proj input / weight rows of 11008
+    ((2, 64, 4096), False),      # K/V [b, s, hidden]
+    ((3, 5, 7, 24), False),      # 4-D per (b, h)
+    ((300, 4096), True),         # layerwise: two-phase long-row path
+    ((4, 40000), False),         # rows too long for registers
+    ((17, 8200), False),         # scalar-path long rows (8200*4 % 16 != 0 for bf16? -> vec for fp32)
+    ((9, 1023), False),          # odd width -> scalar path
+    ((1, 70001), True),
+])
+def test_shapes_and_modes_bit_exact_vs_oracle(dtype, shape, lw):
+    gen = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = (torch.randn(*shape, generator=gen) * 0.5).to(U.DTYPES[dtype])
+    x.view(-1)[::997] *= 9.0
+    xn = U.tensor_to_f32(x)
+    for q, fn in (("sym", qo.sym_forward), ("asym", qo.asym_forward)):
+        for bits in (4, 8):
+            y = _q(q).apply(x.cuda(), CLIP, bits, lw)
+            nm = qo.count_mismatch(U.tensor_to_f32(y), fn(xn, bits, lw, dtype)["y"])
+            assert nm == 0, (q, bits, shape, lw, nm)
+
+
+def test_unaligned_and_noncontiguous_inputs():
+    from llm_qat_b200 import SymQuantizer
+
+    gen = torch.Generator().manual_seed(2)
+    base = torch.randn(64 * 260 + 3, generator=gen).cuda()
+    x = base[3:].view(64, 260)                       # 12-byte offset -> scalar path
+    y = SymQuantizer.apply(x, CLIP, 4, False)
+    assert qo.count_mismatch(U.tensor_to_f32(y), qo.sym_forward(U.tensor_to_f32(x), 4)["y"]) == 0
+    xt = torch.randn(128, 96, generator=gen).cuda().t()   # non-contiguous 2-D: reduce over its last dim
+    y = SymQuantizer.apply(xt, CLIP, 8, False)
+    assert qo.count_mismatch(U.tensor_to_f32(y), qo.sym_forward(U.tensor_to_f32(xt), 8)["y"]) == 0
+    with pytest.raises(ValueError):
+        SymQuantizer.apply(torch.zeros(1, 1, 1, 1, 2).cuda(), CLIP, 4, False)
+    with pytest.raises(RuntimeError):
+        SymQuantizer.apply(torch.zeros(2, 3, 4, 8).cuda().transpose(1, 2), CLIP, 4, False)
+
+
+# --------------------------------------------------------------- full BASELINE sizes: properties
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_config1_full_size_properties(dtype):
+    """[8192, 4096] (BASELINE config 1): size-independent properties + a sampled
+    bit-exact check against the oracle."""
+    from llm_qat_b200 import AsymQuantizer, SymQuantizer
+    from llm_qat_b200._lib import CODES_I16
+    from llm_qat_b200.utils_quant import fake_quant_forward
+
+    gen = torch.Generator().manual_seed(1234)
+    x = (torch.randn(8192, 4096, generator=gen) * 0.5).to(U.DTYPES[dtype]).cuda()
+    g = torch.randn(8192, 4096, generator=gen).to(U.DTYPES[dtype]).cuda()
+    for bits in (4, 8):
+        xr = x.clone().requires_grad_(True)
+        y = SymQuantizer.apply(xr, CLIP, bits, False)
+        y.backward(g)
+        Q = 2 ** (bits - 1) - 1
+        _, codes, s, e, _ = fake_quant_forward(x, bits, False, True, want_y=False, codes_kind=CODES_I16,
+                                               want_scales=True)
+        assert int(codes.abs().max()) in ((Q, Q + 1) if dtype == "bf16" else (Q,))
+        # linearity on the integer grid: y == codes / e exactly (fp32) — the dequant identity
+        if dtype == "fp32":
+            assert torch.equal(y.detach(), codes.float() / e[:, None])
+        # row independence: quantizing a row subset gives the same rows
+        sub = SymQuantizer.apply(x[1000:1064], CLIP, bits, False)
+        assert torch.equal(sub, y.detach()[1000:1064])
+        # checksum of the STE mask: gx is g where |x| < 2, else 0
+        keep = (x.float().abs() < 2.0)
+        assert torch.equal(xr.grad, torch.where(keep, g, torch.zeros_like(g)))
+        # sampled rows vs the oracle
+        rows = torch.arange(0, 8192, 257)
+        o = qo.sym_forward(U.tensor_to_f32(x[rows]), bits, False, dtype)["y"]
+        assert qo.count_mismatch(U.tensor_to_f32(y.detach()[rows]), o) == 0
+        ya = AsymQuantizer.apply(x, CLIP, bits, False)
+        oa = qo.asym_forward(U.tensor_to_f32(x[rows]), bits, False, dtype)["y"]
+        assert qo.count_mismatch(U.tensor_to_f32(ya[rows]), oa) == 0
+        # idempotence of the code grid: re-quantizing y keeps every code (fp32, sym)
+        if dtype == "fp32" and bits == 4:
+            _, codes2, _, _, _ = fake_quant_forward(y.detach(), bits, False, True, want_y=False,
+                                                    codes_kind=CODES_I16)
+            assert torch.equal(codes, codes2)
+
+
+# --------------------------------------------------------------- QuantizeLinear
+@pytest.mark.parametrize("dtype,tol", [("fp32", 5e-6), ("bf16", 1e-2)])
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_quantize_linear_vs_reference_goldens(dtype, tol, fused, monkeypatch):
+    from llm_qat_b200 import QuantizeLinear
+
+    monkeypatch.setenv("QAT_B200_FUSED_LINEAR", fused)
+    g = U.golden(dtype)
+    x0 = U.bits_to_tensor(g["lin/x"], dtype, "cuda")
+    w0 = U.bits_to_tensor(g["lin/w"], dtype, "cuda")
+    gr = U.bits_to_tensor(g["lin/g"], dtype, "cuda")
+    tags = [k.split("/")[-1] for k in g.files if k.startswith("lin/out/")]
+    for tag in tags:
+        body = tag.replace("_wlw", "")
+        w_bits = int(body[1:body.index("a")])
+        rest = body[body.index("a") + 1:]
+        a_bits, sym = int(rest[:-1]), rest[-1] == "s"
+        lin = QuantizeLinear(192, 80, symmetric=sym, w_bits=w_bits, a_bits=a_bits,
+                             weight_layerwise=tag.endswith("_wlw")).to(U.DTYPES[dtype]).cuda()
+        with torch.no_grad():
+            lin.weight.copy_(w0)
+        x = x0.clone().requires_grad_(True)
+        out = lin(x)
+        out.backward(gr)
+        for name, got in (("out", out), ("gx", x.grad), ("gw", lin.weight.grad)):
+            ref = U.bits_to_f32(g[f"lin/{name}/{tag}"], dtype).astype(np.float64)
+            got = U.tensor_to_f32(got).astype(np.float64)
+            rel = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30)
+            assert rel <= tol, (dtype, tag, name, rel, fused)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_lowbit_weight_vs_reference_goldens(dtype):
+    from llm_qat_b200.utils_quant import _LowBitWeight
+
+    g = U.golden(dtype)
+    w = U.bits_to_tensor(g["lowbit/w"], dtype, "cuda")
+    for k in [k for k in g.files if k.startswith("lowbit/weff/")]:
+        tag = k.split("/")[-1]
+        got = _LowBitWeight.apply(w, int(tag[1]), tag.endswith("_lw"))
+        ref = U.bits_to_f32(g[k], dtype)
+        if dtype == "bf16":
+            assert U.mismatches(U.tensor_bits(got), g[k], dtype) == 0, k
+        else:
+            with np.errstate(all="ignore"):
+                rel = np.abs(U.tensor_to_f32(got) - ref) / (np.abs(ref) + 1e-30)
+            assert np.nanmax(rel) < 2e-6, (k, np.nanmax(rel))
+
+
+# --------------------------------------------------------------- K4: tcgen05 GEMM
+@pytest.mark.parametrize("T,N,K", [(128, 256, 128), (256, 512, 4096), (200, 264, 1040), (8, 80, 192),
+                                   (1024, 11008, 4096)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_qlinear_i8_gemm_exact_integer_dot(T, N, K, out_dtype):
+    """int8 x int8 -> s32 is exact, so the only rounding is the epilogue's:
+    compare with an int64 reference scaled in float64."""
+    from llm_qat_b200.utils_quant import qlinear_i8
+
+    gen = torch.Generator().manual_seed(T + N + K)
+    qx = torch.randint(-127, 128, (T, K), generator=gen, dtype=torch.int8)
+    qw = torch.randint(-7, 8, (N, K), generator=gen, dtype=torch.int8)
+    ex = (torch.rand(T, generator=gen) * 50 + 1).float()
+    ew = (torch.rand(N, generator=gen) * 300 + 10).float()
+    out = qlinear_i8(qx.cuda(), qw.cuda(), ex.cuda(), ew.cuda(), out_dtype)
+    acc = qx.double() @ qw.double().t()            # exact: |acc| < 2^53
+    ref = acc / (ex.double()[:, None] * ew.double()[None, :])
+    got = out.double().cpu()
+    tol = 2 ** -8 if out_dtype == torch.bfloat16 else 3e-7
+    err = ((got - ref).abs() / (ref.abs() + 1e-12)).max().item()
+    assert err <= tol, (T, N, K, out_dtype, err)
+
+
+def test_config2_quantize_linear_full_shape():
+    """BASELINE config 2: x bf16 [8192, 4096], W bf16 [11008, 4096], W4A8; fused
+    path vs the unfused (fake-quant kernels + library GEMM) path, rel <= 1e-2."""
+    from llm_qat_b200 import QuantizeLinear
+    import os
+
+    gen = torch.Generator().manual_seed(1234)
+    x = torch.randn(8192, 4096, generator=gen)
+    idx = torch.randint(0, x.numel(), (x.numel() // 1000,), generator=gen)
+    x.view(-1)[idx] *= 20.0
+    x = x.bfloat16().cuda()
+    lin = QuantizeLinear(4096, 11008, w_bits=4, a_bits=8).bfloat16().cuda()
+    with torch.no_grad():
+        lin.weight.copy_((torch.randn(11008, 4096, generator=gen) * 0.02).bfloat16())
+    outs = {}
+    for fused in ("0", "1"):
+        os.environ["QAT_B200_FUSED_LINEAR"] = fused
+        with torch.no_grad():
+            outs[fused] = lin(x).float()
+    os.environ.pop("QAT_B200_FUSED_LINEAR")
+    rel = (outs["1"] - outs["0"]).norm() / outs["0"].norm()
+    assert rel.item() <= 1e-2, rel.item()
+    rows = (outs["1"] - outs["0"]).norm(dim=1) / outs["0"].norm(dim=1)
+    assert rows.max().item() <= 1e-2, rows.max().item()
+
+
+# --------------------------------------------------------------- host-buffer entry points
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("sym", [True, False])
+def test_host_entry_points_match_device_path(dtype, sym):
+    from llm_qat_b200.host_api import fake_quant_fwd_bwd_host
+
+    gen = torch.Generator().manual_seed(9)
+    x = (torch.randn(3000, 4096, generator=gen) * 0.8).to(U.DTYPES[dtype]).pin_memory()
+    g = torch.randn(3000, 4096, generator=gen).to(U.DTYPES[dtype]).pin_memory()
+    y, gx = fake_quant_fwd_bwd_host(x, g, (-2.0, 2.0), 8, symmetric=sym)
+    torch.cuda.synchronize()
+    rows = torch.arange(0, 3000, 37)
+    fn = qo.sym_forward if sym else qo.asym_forward
+    assert qo.count_mismatch(U.tensor_to_f32(y[rows]), fn(U.tensor_to_f32(x[rows]), 8, False, dtype)["y"]) == 0
+    ob = qo.ste_backward(U.tensor_to_f32(g), U.tensor_to_f32(x), -2.0, 2.0, dtype)
+    assert qo.count_mismatch(U.tensor_to_f32(gx), ob["gx"]) == 0
