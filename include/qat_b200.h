@@ -134,6 +134,16 @@ int qat_asym_fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, 
                           float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
                           int bits, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
+/*
+ * Device self-test of the hoisted-reciprocal divisions K1/K2 use in place of a
+ * per-element div.rn (see csrc/common.cuh): `rows` random divisors in
+ * [2^-100, 2^100], `per_row` numerators each (general in [0, b] and integer
+ * codes |q| <= 32767).  dev_counters[4] (caller-zeroed device u64):
+ * {general mismatches, general tested, integer mismatches, integer tested}.
+ */
+int qat_selftest_fastdiv(uint64_t seed, int64_t rows, int per_row, int bf16_operands,
+                         uint64_t* dev_counters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,8 @@ def _declare(lib):
         "qat_lowbit_weight_fwd": (I, [P, P, L, L, I, I, I, P, Z, P]),
         # qx, qw, ex, ew, out, T, N, K, out_dtype, stream
         "qat_qlinear_i8_fwd": (I, [P, P, P, P, P, L, L, L, I, P]),
+        # seed, rows, per_row, bf16_operands, dev_counters, stream
+        "qat_selftest_fastdiv": (I, [c_uint64, L, I, I, P, P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
         "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),

@@ -149,13 +149,23 @@ __device__ __forceinline__ float load_scalar(const void* x, int64_t i) {
 
 // ---- per-vector quantize + all outputs ------------------------------------
 // `e0` = flat element index of the vector's first element.
-template <int DT, bool SYM, typename Scale>
+template <int DT, bool SYM, bool FAST, typename Scale>
 __device__ __forceinline__ void emit_vec(const FwdParams& p, const Scale& sc, const uint4& v,
                                          int64_t e0, bool valid) {
   constexpr int N = Num<DT>::kPerVec;
   float yv[N], qv[N];
+  if constexpr (SYM && DT == QAT_BF16) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < N; ++i) yv[i] = sc.apply(vec_get<DT>(v, i), &qv[i]);
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t pw = mul_bf16x2(w[j], sc.s2);  // fl_bf16(x * s), two elements
+      yv[(2 * j) % N] = sc.template apply_p<FAST>(bf16lo(pw), &qv[(2 * j) % N]);
+      yv[(2 * j + 1) % N] = sc.template apply_p<FAST>(bf16hi(pw), &qv[(2 * j + 1) % N]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) yv[i] = sc.template apply<FAST>(vec_get<DT>(v, i), &qv[i]);
+  }
   if (p.y != nullptr && valid) {
     uint4 o;
     if (DT == QAT_F32) {
@@ -217,11 +227,11 @@ __device__ __forceinline__ void emit_vec(const FwdParams& p, const Scale& sc, co
   }
 }
 
-template <int DT, bool SYM, typename Scale>
+template <int DT, bool SYM, bool FAST, typename Scale>
 __device__ __forceinline__ void emit_scalar(const FwdParams& p, const Scale& sc, float xf,
                                             int64_t e0) {
   float q;
-  float yf = sc.apply(xf, &q);
+  float yf = sc.template apply<FAST>(xf, &q);
   if (p.y != nullptr) {
     if (DT == QAT_F32)
       reinterpret_cast<float*>(p.y)[e0] = yf;
@@ -306,11 +316,18 @@ __global__ void __launch_bounds__(1024) rowquant_kernel(const FwdParams p) {
       if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
       if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
     }
+    if (sc.fast) {  // row-uniform (=> warp-uniform: a warp never spans two rows)
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int64_t j = t + (int64_t)i * group;
-      const bool valid = row_ok && j < p.nvec;
-      emit_vec<DT, SYM>(p, sc, v[i], row_e0 + j * Num<DT>::kPerVec, valid);
+      for (int i = 0; i < ITERS; ++i) {
+        const int64_t j = t + (int64_t)i * group;
+        emit_vec<DT, SYM, true>(p, sc, v[i], row_e0 + j * Num<DT>::kPerVec, row_ok && j < p.nvec);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int64_t j = t + (int64_t)i * group;
+        emit_vec<DT, SYM, false>(p, sc, v[i], row_e0 + j * Num<DT>::kPerVec, row_ok && j < p.nvec);
+      }
     }
   } else {
     float v[ITERS];
@@ -333,7 +350,12 @@ __global__ void __launch_bounds__(1024) rowquant_kernel(const FwdParams p) {
 #pragma unroll
     for (int i = 0; i < ITERS; ++i) {
       const int64_t j = t + (int64_t)i * group;
-      if (row_ok && j < p.nvec) emit_scalar<DT, SYM>(p, sc, v[i], row_e0 + j);
+      if (row_ok && j < p.nvec) {
+        if (sc.fast)
+          emit_scalar<DT, SYM, true>(p, sc, v[i], row_e0 + j);
+        else
+          emit_scalar<DT, SYM, false>(p, sc, v[i], row_e0 + j);
+      }
     }
   }
 }
@@ -426,11 +448,18 @@ __global__ void __launch_bounds__(256) longrow_apply_kernel(const FwdParams p) {
       const int64_t j = jb + threadIdx.x;
       const bool valid = j < j1;
       uint4 v = valid ? ldg_stream(xrow + j * 16) : make_uint4(0u, 0u, 0u, 0u);
-      emit_vec<DT, SYM>(p, sc, v, row_e0 + j * Num<DT>::kPerVec, valid);
+      if (sc.fast)
+        emit_vec<DT, SYM, true>(p, sc, v, row_e0 + j * Num<DT>::kPerVec, valid);
+      else
+        emit_vec<DT, SYM, false>(p, sc, v, row_e0 + j * Num<DT>::kPerVec, valid);
     }
   } else {
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += 256)
-      emit_scalar<DT, SYM>(p, sc, load_scalar<DT>(p.x, row_e0 + j), row_e0 + j);
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += 256) {
+      if (sc.fast)
+        emit_scalar<DT, SYM, true>(p, sc, load_scalar<DT>(p.x, row_e0 + j), row_e0 + j);
+      else
+        emit_scalar<DT, SYM, false>(p, sc, load_scalar<DT>(p.x, row_e0 + j), row_e0 + j);
+    }
   }
 }
 

@@ -61,6 +61,24 @@ def test_backward_bit_exact_vs_reference_goldens(dtype):
     assert not bad, bad
 
 
+# --------------------------------------------------------------- hoisted-reciprocal division
+@pytest.mark.parametrize("bf16_operands", [0, 1])
+def test_fast_division_matches_div_rn_on_device(bf16_operands):
+    """K1/K2 replace the per-element div.rn by 3 FP ops on a per-row reciprocal;
+    ~2.7e9 random operand pairs (x2 kinds) must agree with div.rn bit for bit."""
+    import llm_qat_b200
+
+    L = llm_qat_b200._lib.lib()
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    for seed in (1, 2):
+        rc = L.qat_selftest_fastdiv(seed * 7919, 1 << 20, 1280, bf16_operands, counters.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream)
+        llm_qat_b200._lib.check(rc, "qat_selftest_fastdiv")
+    bad, n, bad_i, n_i = counters.tolist()
+    assert n > 2e9 and n_i > 2e9, (n, n_i)
+    assert bad == 0 and bad_i == 0, (bad, n, bad_i, n_i)
+
+
 # --------------------------------------------------------------- codes, scales, masks vs oracle
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("sym", [True, False])
