@@ -136,10 +136,14 @@ int qat_asym_fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, 
 
 /*
  * Device self-test of the hoisted-reciprocal divisions K1/K2 use in place of a
- * per-element div.rn (see csrc/common.cuh): `rows` random divisors in
- * [2^-100, 2^100], `per_row` numerators each (general in [0, b] and integer
- * codes |q| <= 32767).  dev_counters[4] (caller-zeroed device u64):
- * {general mismatches, general tested, integer mismatches, integer tested}.
+ * per-element div.rn (see csrc/common.cuh): `rows` random divisors, `per_row`
+ * numerators each.  dev_counters[6] (caller-zeroed device u64):
+ * {general-numerator mismatches, tested}  divisor in [2^-27, 2^100] (the Asym
+ *                                         row guard), quotient in [2^-41, 1];
+ * {integer-code mismatches, tested}       |q| <= 32767, divisor in [2^-100, 2^100];
+ * {wide-domain mismatches, tested}        informational: numerators down to the
+ *                                         denormal boundary, outside what the
+ *                                         kernels rely on.
  */
 int qat_selftest_fastdiv(uint64_t seed, int64_t rows, int per_row, int bf16_operands,
                          uint64_t* dev_counters, void* stream);

@@ -32,6 +32,7 @@ struct FwdParams {
   int64_t nvec;  // vectors (VEC) or elements (scalar path) per row
   float qmax;    // Sym: Q = 2^(bits-1)-1     Asym: S = 2^bits-1
   int group;     // threads cooperating on one row (power of two, >= 32)
+  int log2_group;
   // long-row path
   uint32_t* ws;
   int64_t chunk;  // vectors per CTA
@@ -275,11 +276,218 @@ struct ScaleOf<DT, false> {
 // K1 / K2: one row per thread group, the row lives in registers between the
 // reduction and the quantize pass => exactly one HBM read + one HBM write.
 //   grid  = ceil(rows / (blockDim / group)),  block = max(group, 256)
-//   ITERS = 16-byte vectors (or scalars) per thread, compile-time unrolled so
-//           all loads of a row are in flight before the first use.
+//   ITERS = 16-byte vectors per thread, compile-time unrolled so all loads of a
+//           row are in flight before the first use.
+//   OUT   = which outputs exist, resolved at compile time so the element loop
+//           carries no branches:  OUT_Y (y [+ scales]) is Quantizer.apply;
+//           OUT_FEED (int8 codes + scales [+ mask], no y) feeds the tcgen05 GEMM;
+//           OUT_ANY keeps every output optional at run time.
+// The kernel is instruction-issue bound in bf16 (4 B/elem of traffic), hence:
+// 32-bit in-row indexing, one lane per warp derives the scale (two frcp.rn) and
+// shuffles it, packed bf16x2 multiply and packed sign restoration.
 // =============================================================================
-template <int DT, int ITERS, bool SYM, bool VEC>
-__global__ void __launch_bounds__(1024) rowquant_kernel(const FwdParams p) {
+constexpr int OUT_Y = 0, OUT_FEED = 1, OUT_ANY = 2;
+
+template <int DT, bool SYM>
+__device__ __forceinline__ typename ScaleOf<DT, SYM>::type warp_derive_scale(const RowStat& st, float qmax) {
+  using SO = ScaleOf<DT, SYM>;
+  typename SO::type sc;
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) sc = SO::make(st, qmax);
+  if constexpr (SYM) {
+    sc.s = __shfl_sync(kFull, sc.s, 0);
+    sc.e = __shfl_sync(kFull, sc.e, 0);
+    sc.r = __shfl_sync(kFull, sc.r, 0);
+    sc.s2 = pack_bf16x2(sc.s, sc.s);
+    sc.fast = recip_range_ok(sc.e);
+  } else {
+    sc.a = __shfl_sync(kFull, sc.a, 0);
+    sc.beta = __shfl_sync(kFull, sc.beta, 0);
+    sc.ra.r1 = __shfl_sync(kFull, sc.ra.r1, 0);
+    sc.S = qmax;
+    sc.rS = __shfl_sync(kFull, sc.rS, 0);
+    sc.fast = recip_range_ok(sc.a) && (sc.beta == sc.beta);
+  }
+  return sc;
+}
+
+// y for one 16-byte vector, no side outputs (the Quantizer.apply hot loop)
+template <int DT, bool SYM, bool FAST, typename Scale>
+__device__ __forceinline__ uint4 quant_vec_y(const Scale& sc, const uint4& v) {
+  uint4 o;
+  if constexpr (SYM && DT == QAT_BF16) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t pw = mul_bf16x2(w[j], sc.s2);  // fl_bf16(x * s), two elements
+      const float c0 = rintf(bf16lo(pw)), c1 = rintf(bf16hi(pw));
+      if (FAST) {
+        // sign(y) == sign(p) always (e > 0); restoring it on the packed pair also
+        // turns the +0 that the remainder step gives for c = -0 back into -0.
+        ow[j] = pack_bf16x2(div_code_by_recip(c0, sc.e, sc.r), div_code_by_recip(c1, sc.e, sc.r)) |
+                (pw & 0x80008000u);
+      } else {
+        ow[j] = pack_bf16x2(__fdiv_rn(c0, sc.e), __fdiv_rn(c1, sc.e));
+      }
+    }
+    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  } else {
+    constexpr int N = Num<DT>::kPerVec;
+    float yv[N], q;
+#pragma unroll
+    for (int i = 0; i < N; ++i) yv[i] = sc.template apply<FAST>(vec_get<DT>(v, i), &q);
+    if (DT == QAT_F32) {
+      o = make_uint4(__float_as_uint(yv[0]), __float_as_uint(yv[1]), __float_as_uint(yv[2]),
+                     __float_as_uint(yv[3]));
+    } else {
+      o = make_uint4(pack_bf16x2(yv[0], yv[1]), pack_bf16x2(yv[2 % N], yv[3 % N]),
+                     pack_bf16x2(yv[4 % N], yv[5 % N]), pack_bf16x2(yv[6 % N], yv[7 % N]));
+    }
+  }
+  return o;
+}
+
+// int8 codes (+ optional packed mask) for one vector: the GEMM feed.  Only the
+// code is needed, so Sym does no division at all.
+template <int DT, bool SYM, bool FAST, typename Scale>
+__device__ __forceinline__ void quant_vec_feed(const FwdParams& p, const Scale& sc, const uint4& v,
+                                               uint8_t* codes_row, uint8_t* mask_row, uint32_t j,
+                                               bool valid) {
+  constexpr int N = Num<DT>::kPerVec;
+  float qv[N];
+  if constexpr (SYM && DT == QAT_BF16) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t pw = mul_bf16x2(w[k], sc.s2);
+      qv[(2 * k) % N] = rintf(bf16lo(pw));
+      qv[(2 * k + 1) % N] = rintf(bf16hi(pw));
+    }
+  } else if constexpr (SYM) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) qv[i] = rintf(Num<DT>::fl(__fmul_rn(vec_get<DT>(v, i), sc.s)));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) (void)sc.template apply<FAST>(vec_get<DT>(v, i), &qv[i]);
+  }
+  uint32_t cw[N / 4];
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i)
+    cw[i] = (uint32_t)code_i8<SYM>(qv[4 * i]) | ((uint32_t)code_i8<SYM>(qv[4 * i + 1]) << 8) |
+            ((uint32_t)code_i8<SYM>(qv[4 * i + 2]) << 16) | ((uint32_t)code_i8<SYM>(qv[4 * i + 3]) << 24);
+  if (valid) {
+    if (N == 4)
+      *reinterpret_cast<uint32_t*>(codes_row + (size_t)j * N) = cw[0];
+    else
+      *reinterpret_cast<uint2*>(codes_row + (size_t)j * N) = make_uint2(cw[0], cw[(N / 4) - 1]);
+  }
+  if (mask_row != nullptr) {
+    uint32_t pass = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float xf = vec_get<DT>(v, i);
+      pass |= ((xf >= p.hi || xf <= p.lo) ? 0u : 1u) << i;  // utils_quant.py:85-86
+    }
+    if (N == 8) {
+      if (valid) mask_row[j] = (uint8_t)pass;
+    } else {
+      const uint32_t mine = valid ? pass : 0u;
+      const uint32_t other = __shfl_xor_sync(kFull, mine, 1);
+      if (valid && !(threadIdx.x & 1)) mask_row[j >> 1] = (uint8_t)(mine | (other << 4));
+    }
+  }
+}
+
+template <int DT, int ITERS, bool SYM, int OUT>
+__global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
+  __shared__ uint32_t sm_u[32];
+  __shared__ float sm_mx[32], sm_mn[32];
+
+  const uint32_t lg = (uint32_t)p.log2_group;
+  const uint32_t group = 1u << lg;
+  const uint32_t t = threadIdx.x & (group - 1u);
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> lg) + (threadIdx.x >> lg);
+  const bool row_ok = row < p.rows;
+  const uint32_t nvec = row_ok ? (uint32_t)p.nvec : 0u;  // fused rows hold <= 8192 vectors
+  const uint4* xrow = reinterpret_cast<const uint4*>(p.x) + row * p.nvec;
+
+  uint4 v[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const uint32_t j = t + (uint32_t)i * group;
+    v[i] = (j < nvec) ? ldg_stream(xrow + j) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  RowStat st = stat_identity();
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const uint32_t j = t + (uint32_t)i * group;
+    if (SYM || j < nvec) accumulate_vec<DT, SYM>(st, v[i]);  // zero vectors are neutral for max|x|
+  }
+  finalize_thread_stat<DT, SYM, true>(st);
+  group_reduce<SYM>(st, (int)group, sm_u, sm_mx, sm_mn);
+  using SO = ScaleOf<DT, SYM>;
+  const typename SO::type sc = warp_derive_scale<DT, SYM>(st, p.qmax);
+  if (t == 0 && row_ok) {
+    if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
+    if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
+  }
+
+  if constexpr (OUT == OUT_Y) {
+    uint4* yrow = reinterpret_cast<uint4*>(p.y) + row * p.nvec;
+    if (sc.fast) {  // row-uniform => warp-uniform: a warp never spans two rows
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const uint32_t j = t + (uint32_t)i * group;
+        const uint4 o = quant_vec_y<DT, SYM, true>(sc, v[i]);
+        if (j < nvec) stg_stream(yrow + j, o);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const uint32_t j = t + (uint32_t)i * group;
+        const uint4 o = quant_vec_y<DT, SYM, false>(sc, v[i]);
+        if (j < nvec) stg_stream(yrow + j, o);
+      }
+    }
+  } else if constexpr (OUT == OUT_FEED) {
+    uint8_t* codes_row = reinterpret_cast<uint8_t*>(p.codes) + row * p.cols;
+    uint8_t* mask_row = p.mask != nullptr ? p.mask + ((row * p.cols) >> 3) : nullptr;
+    if (sc.fast) {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const uint32_t j = t + (uint32_t)i * group;
+        quant_vec_feed<DT, SYM, true>(p, sc, v[i], codes_row, mask_row, j, j < nvec);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const uint32_t j = t + (uint32_t)i * group;
+        quant_vec_feed<DT, SYM, false>(p, sc, v[i], codes_row, mask_row, j, j < nvec);
+      }
+    }
+  } else {
+    const int64_t row_e0 = row * p.cols;
+    if (sc.fast) {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const uint32_t j = t + (uint32_t)i * group;
+        emit_vec<DT, SYM, true>(p, sc, v[i], row_e0 + (int64_t)j * Num<DT>::kPerVec, j < nvec);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const uint32_t j = t + (uint32_t)i * group;
+        emit_vec<DT, SYM, false>(p, sc, v[i], row_e0 + (int64_t)j * Num<DT>::kPerVec, j < nvec);
+      }
+    }
+  }
+}
+
+// scalar path (misaligned pointers or row pitch not a multiple of 16 bytes):
+// same structure, one element per thread-iteration, every output optional.
+template <int DT, int ITERS, bool SYM>
+__global__ void __launch_bounds__(1024) rowquant_scalar_kernel(const FwdParams p) {
   __shared__ uint32_t sm_u[32];
   __shared__ float sm_mx[32], sm_mn[32];
 
@@ -288,74 +496,33 @@ __global__ void __launch_bounds__(1024) rowquant_kernel(const FwdParams p) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x / group) + (threadIdx.x / group);
   const bool row_ok = row < p.rows;
   const int64_t row_e0 = row * p.cols;
-
   RowStat st = stat_identity();
   using SO = ScaleOf<DT, SYM>;
-
-  if (VEC) {
-    uint4 v[ITERS];
-    const char* xrow = reinterpret_cast<const char*>(p.x) + row_e0 * Num<DT>::kBytes;
+  float v[ITERS];
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int64_t j = t + (int64_t)i * group;
-      if (row_ok && j < p.nvec) {
-        v[i] = ldg_stream(xrow + j * 16);
-      } else {
-        v[i] = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
+  for (int i = 0; i < ITERS; ++i) {
+    const int64_t j = t + (int64_t)i * group;
+    v[i] = (row_ok && j < p.nvec) ? load_scalar<DT>(p.x, row_e0 + j) : 0.f;
+  }
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int64_t j = t + (int64_t)i * group;
-      if (SYM || (row_ok && j < p.nvec)) accumulate_vec<DT, SYM>(st, v[i]);  // zeros are neutral for |x|
-    }
-    finalize_thread_stat<DT, SYM, VEC>(st);
-    group_reduce<SYM>(st, group, sm_u, sm_mx, sm_mn);
-    const typename SO::type sc = SO::make(st, p.qmax);
-    if (t == 0 && row_ok) {
-      if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
-      if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
-    }
-    if (sc.fast) {  // row-uniform (=> warp-uniform: a warp never spans two rows)
+  for (int i = 0; i < ITERS; ++i) {
+    const int64_t j = t + (int64_t)i * group;
+    if (row_ok && j < p.nvec) accumulate_scalar<DT, SYM>(st, v[i]);
+  }
+  group_reduce<SYM>(st, group, sm_u, sm_mx, sm_mn);
+  const typename SO::type sc = SO::make(st, p.qmax);
+  if (t == 0 && row_ok) {
+    if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
+    if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
+  }
 #pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int64_t j = t + (int64_t)i * group;
-        emit_vec<DT, SYM, true>(p, sc, v[i], row_e0 + j * Num<DT>::kPerVec, row_ok && j < p.nvec);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int64_t j = t + (int64_t)i * group;
-        emit_vec<DT, SYM, false>(p, sc, v[i], row_e0 + j * Num<DT>::kPerVec, row_ok && j < p.nvec);
-      }
-    }
-  } else {
-    float v[ITERS];
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int64_t j = t + (int64_t)i * group;
-      v[i] = (row_ok && j < p.nvec) ? load_scalar<DT>(p.x, row_e0 + j) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int64_t j = t + (int64_t)i * group;
-      if (row_ok && j < p.nvec) accumulate_scalar<DT, SYM>(st, v[i]);
-    }
-    group_reduce<SYM>(st, group, sm_u, sm_mx, sm_mn);
-    const typename SO::type sc = SO::make(st, p.qmax);
-    if (t == 0 && row_ok) {
-      if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
-      if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
-    }
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int64_t j = t + (int64_t)i * group;
-      if (row_ok && j < p.nvec) {
-        if (sc.fast)
-          emit_scalar<DT, SYM, true>(p, sc, v[i], row_e0 + j);
-        else
-          emit_scalar<DT, SYM, false>(p, sc, v[i], row_e0 + j);
-      }
+  for (int i = 0; i < ITERS; ++i) {
+    const int64_t j = t + (int64_t)i * group;
+    if (row_ok && j < p.nvec) {
+      if (sc.fast)
+        emit_scalar<DT, SYM, true>(p, sc, v[i], row_e0 + j);
+      else
+        emit_scalar<DT, SYM, false>(p, sc, v[i], row_e0 + j);
     }
   }
 }
@@ -502,26 +669,43 @@ Plan make_plan(const void* x, const void* y, int64_t rows, int64_t cols, int dty
   return pl;
 }
 
+template <int DT, bool SYM, int ITERS>
+void launch_vec_iters(const FwdParams& p, const Plan& pl, unsigned grid, int out, cudaStream_t st) {
+  if (out == OUT_Y)
+    rowquant_vec_kernel<DT, ITERS, SYM, OUT_Y><<<grid, pl.block, 0, st>>>(p);
+  else if (out == OUT_FEED)
+    rowquant_vec_kernel<DT, ITERS, SYM, OUT_FEED><<<grid, pl.block, 0, st>>>(p);
+  else
+    rowquant_vec_kernel<DT, ITERS, SYM, OUT_ANY><<<grid, pl.block, 0, st>>>(p);
+}
+
 template <int DT, bool SYM, bool VEC>
 int launch_fused(const FwdParams& p, const Plan& pl, cudaStream_t st) {
   const int rows_per_cta = pl.block / pl.group;
-  const int64_t grid = (p.rows + rows_per_cta - 1) / rows_per_cta;
-  if (grid > 0x7fffffffLL) {
+  const int64_t grid64 = (p.rows + rows_per_cta - 1) / rows_per_cta;
+  if (grid64 > 0x7fffffffLL) {
     set_error("too many rows (%lld)", (long long)p.rows);
     return QAT_ERR_UNSUPPORTED;
   }
-  switch (pl.iters) {
-    case 2:
-      rowquant_kernel<DT, 2, SYM, VEC><<<(unsigned)grid, pl.block, 0, st>>>(p);
-      break;
-    case 4:
-      rowquant_kernel<DT, 4, SYM, VEC><<<(unsigned)grid, pl.block, 0, st>>>(p);
-      break;
-    default:
-      rowquant_kernel<DT, 8, SYM, VEC><<<(unsigned)grid, pl.block, 0, st>>>(p);
-      break;
+  const unsigned grid = (unsigned)grid64;
+  if (VEC) {
+    int out = OUT_ANY;
+    if (p.y != nullptr && p.codes == nullptr && p.mask == nullptr) out = OUT_Y;
+    if (p.y == nullptr && p.codes != nullptr && p.codes_kind == QAT_CODES_I8) out = OUT_FEED;
+    switch (pl.iters) {
+      case 2: launch_vec_iters<DT, SYM, 2>(p, pl, grid, out, st); break;
+      case 4: launch_vec_iters<DT, SYM, 4>(p, pl, grid, out, st); break;
+      default: launch_vec_iters<DT, SYM, 8>(p, pl, grid, out, st); break;
+    }
+    QAT_CHECK_LAUNCH("rowquant_vec_kernel");
+  } else {
+    switch (pl.iters) {
+      case 2: rowquant_scalar_kernel<DT, 2, SYM><<<grid, pl.block, 0, st>>>(p); break;
+      case 4: rowquant_scalar_kernel<DT, 4, SYM><<<grid, pl.block, 0, st>>>(p); break;
+      default: rowquant_scalar_kernel<DT, 8, SYM><<<grid, pl.block, 0, st>>>(p); break;
+    }
+    QAT_CHECK_LAUNCH("rowquant_scalar_kernel");
   }
-  QAT_CHECK_LAUNCH("rowquant_kernel");
   return QAT_OK;
 }
 
@@ -604,6 +788,8 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
   p.nvec = pl.nvec;
   p.qmax = SYM ? (float)((1 << (bits - 1)) - 1) : (float)((1 << bits) - 1);
   p.group = pl.group;
+  p.log2_group = 0;
+  while ((1 << p.log2_group) < pl.group) ++p.log2_group;
   p.ws = reinterpret_cast<uint32_t*>(workspace);
   p.chunk = pl.chunk;
   if (!pl.fused) {

@@ -69,12 +69,13 @@ def test_fast_division_matches_div_rn_on_device(bf16_operands):
     import llm_qat_b200
 
     L = llm_qat_b200._lib.lib()
-    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    counters = torch.zeros(6, dtype=torch.int64, device="cuda")
     for seed in (1, 2):
         rc = L.qat_selftest_fastdiv(seed * 7919, 1 << 20, 1280, bf16_operands, counters.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream)
         llm_qat_b200._lib.check(rc, "qat_selftest_fastdiv")
-    bad, n, bad_i, n_i = counters.tolist()
+    bad, n, bad_i, n_i, bad_w, n_w = counters.tolist()
+    print(f"fastdiv self-test: general {bad}/{n}, integer {bad_i}/{n_i}, wide (informational) {bad_w}/{n_w}")
     assert n > 2e9 and n_i > 2e9, (n, n_i)
     assert bad == 0 and bad_i == 0, (bad, n, bad_i, n_i)
 
