@@ -123,6 +123,15 @@ int qat_lowbit_weight_fwd(const void* w, void* w_eff, int64_t rows, int64_t cols
 int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const float* ex, const float* ew,
                        void* out, int64_t T, int64_t N, int64_t K, int out_dtype, void* stream);
 
+/*
+ * Rebuild the fake-quantized tensor from K1's int8 codes and row divisors:
+ * out[r,c] = fl(codes[r,c] / row_e[r]) — bit-identical to qat_sym_fwd's y
+ * (utils_quant.py:72) wherever the int8 feed did not saturate.  cols % 16 == 0.
+ * Used by QuantizeLinear's backward for the dgrad / wgrad operands.
+ */
+int qat_dequant_codes(const int8_t* codes, const float* row_e, void* out, int64_t rows, int64_t cols,
+                      int dtype, void* stream);
+
 /* Host-buffer convenience entry points (pinned or pageable host memory):
  * copy in, run, copy out on `stream`; `dev_scratch` must hold
  * qat_host_scratch_bytes(...) bytes of device memory. */

@@ -42,6 +42,8 @@ def _declare(lib):
         "qat_qlinear_i8_fwd": (I, [P, P, P, P, P, L, L, L, I, P]),
         # seed, rows, per_row, bf16_operands, dev_counters, stream
         "qat_selftest_fastdiv": (I, [c_uint64, L, I, I, P, P]),
+        # codes, row_e, out, rows, cols, dtype, stream
+        "qat_dequant_codes": (I, [P, P, P, L, L, I, P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
         "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),

@@ -11,6 +11,8 @@
 //
 // HBM-bound: algorithmic traffic = 2*sizeof(T) bytes per element (+1/8 B with
 // the mask, +1 or 2 B with codes).  See DESIGN.md section "K1/K2".
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace qat {
@@ -411,6 +413,9 @@ __global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
   const bool row_ok = row < p.rows;
   const uint32_t nvec = row_ok ? (uint32_t)p.nvec : 0u;  // fused rows hold <= 8192 vectors
   const uint4* xrow = reinterpret_cast<const uint4*>(p.x) + row * p.nvec;
+  // keep the 64-bit row base in registers: without this the compiler re-derives
+  // row * nvec under every load's predicate (5 extra instructions per vector)
+  asm volatile("" : "+l"(xrow));
 
   uint4 v[ITERS];
 #pragma unroll
@@ -435,6 +440,7 @@ __global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
 
   if constexpr (OUT == OUT_Y) {
     uint4* yrow = reinterpret_cast<uint4*>(p.y) + row * p.nvec;
+    asm volatile("" : "+l"(yrow));
     if (sc.fast) {  // row-uniform => warp-uniform: a warp never spans two rows
 #pragma unroll
       for (int i = 0; i < ITERS; ++i) {
@@ -636,6 +642,16 @@ constexpr int kMaxGroup = 1024;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// tuning knob (development): QAT_B200_MAX_ITERS=1..8 caps the vectors per thread
+int tuned_max_iters() {
+  static int v = [] {
+    const char* e = getenv("QAT_B200_MAX_ITERS");
+    int n = e ? atoi(e) : kMaxIters;
+    return (n >= 1 && n <= kMaxIters) ? n : kMaxIters;
+  }();
+  return v;
+}
+
 struct Plan {
   bool vec;
   bool fused;  // row fits registers
@@ -650,15 +666,32 @@ Plan make_plan(const void* x, const void* y, int64_t rows, int64_t cols, int dty
   const int per = 16 / esz;
   pl.vec = (cols % per == 0) && aligned16(x) && (y == nullptr || aligned16(y));
   pl.nvec = pl.vec ? cols / per : cols;
-  // smallest power-of-two group (>=32) that keeps <= 4 vectors per thread,
-  // falling back to up to 8 per thread at the 1024-thread cap.
-  int group = 32;
-  while (group < kMaxGroup && (pl.nvec + group - 1) / group > 4) group <<= 1;
-  int64_t iters = (pl.nvec + group - 1) / group;
-  pl.fused = iters <= kMaxIters;
-  pl.group = group;
-  pl.iters = iters <= 2 ? 2 : iters <= 4 ? 4 : 8;
-  pl.block = group < 256 ? 256 : group;
+  // Threads per row (power of two >= 32) and vectors per thread (<= 8).  Per-thread
+  // fixed work (reduction tree, scale broadcast, addressing) is ~200 instructions,
+  // so prefer many vectors per thread; among candidates take the one with the
+  // fewest idle vector slots, ties to the smaller group.
+  const int max_iters = tuned_max_iters();
+  int best_group = 0;
+  int64_t best_iters = 0, best_slots = 0;
+  for (int group = 32; group <= kMaxGroup; group <<= 1) {
+    const int64_t iters = (pl.nvec + group - 1) / group;
+    if (iters > max_iters) continue;
+    const int64_t slots = iters * group;
+    if (best_group == 0 || slots < best_slots) {
+      best_group = group;
+      best_iters = iters;
+      best_slots = slots;
+    }
+  }
+  pl.fused = best_group != 0;
+  if (!pl.fused) {  // does not fit: the cap below only sizes the long-row path
+    best_group = kMaxGroup;
+    best_iters = kMaxIters;
+  }
+  pl.group = best_group;
+  pl.iters = (int)best_iters;
+  if (!pl.vec) pl.iters = best_iters <= 2 ? 2 : best_iters <= 4 ? 4 : 8;  // scalar kernels: 3 instantiations
+  pl.block = best_group < 256 ? 256 : best_group;
   if (!pl.fused) {
     int64_t chunk = (pl.nvec + 4095) / 4096;
     if (chunk < 2048) chunk = 2048;
@@ -693,8 +726,13 @@ int launch_fused(const FwdParams& p, const Plan& pl, cudaStream_t st) {
     if (p.y != nullptr && p.codes == nullptr && p.mask == nullptr) out = OUT_Y;
     if (p.y == nullptr && p.codes != nullptr && p.codes_kind == QAT_CODES_I8) out = OUT_FEED;
     switch (pl.iters) {
+      case 1: launch_vec_iters<DT, SYM, 1>(p, pl, grid, out, st); break;
       case 2: launch_vec_iters<DT, SYM, 2>(p, pl, grid, out, st); break;
+      case 3: launch_vec_iters<DT, SYM, 3>(p, pl, grid, out, st); break;
       case 4: launch_vec_iters<DT, SYM, 4>(p, pl, grid, out, st); break;
+      case 5: launch_vec_iters<DT, SYM, 5>(p, pl, grid, out, st); break;
+      case 6: launch_vec_iters<DT, SYM, 6>(p, pl, grid, out, st); break;
+      case 7: launch_vec_iters<DT, SYM, 7>(p, pl, grid, out, st); break;
       default: launch_vec_iters<DT, SYM, 8>(p, pl, grid, out, st); break;
     }
     QAT_CHECK_LAUNCH("rowquant_vec_kernel");
@@ -816,7 +854,7 @@ size_t qat_fwd_workspace_bytes(int64_t rows, int64_t cols, int dtype) {
   (void)dtype;
   // the scalar path may be chosen at run time when a pointer is misaligned, so
   // size for it: fused iff cols <= kMaxGroup * kMaxIters elements.
-  if (cols <= (int64_t)qat::kMaxGroup * qat::kMaxIters) return 0;
+  if (cols <= (int64_t)qat::kMaxGroup * qat::tuned_max_iters()) return 0;
   return (size_t)rows * 16;
 }
 

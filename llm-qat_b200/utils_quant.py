@@ -17,8 +17,8 @@ Install under the reference's import name before its model file is imported::
     from models.modeling_llama_quant import LlamaForCausalLM
 
 Run-time knobs (environment; signatures stay the reference's):
-  QAT_B200_FUSED_LINEAR=0|1   QuantizeLinear uses the integer-grid tcgen05 GEMM (default 0 for now; 1
-                              when shapes/dtypes allow) or fake-quant kernels + F.linear.
+  QAT_B200_FUSED_LINEAR=0|1   QuantizeLinear uses the integer-grid tcgen05 GEMM (default 1, taken
+                              when shapes/dtypes allow) or the fake-quant kernels + F.linear (0).
 """
 from __future__ import annotations
 
@@ -224,7 +224,7 @@ class _LowBitWeight(torch.autograd.Function):
 
 # ------------------------------------------------------------------ fused linear
 def _fused_linear_enabled() -> bool:
-    return os.environ.get("QAT_B200_FUSED_LINEAR", "0") == "1"
+    return os.environ.get("QAT_B200_FUSED_LINEAR", "1") != "0"
 
 
 class _QuantLinearFn(torch.autograd.Function):
@@ -264,12 +264,24 @@ class _QuantLinearFn(torch.autograd.Function):
         g2 = g2 if g2.is_contiguous() else g2.contiguous()
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            wq = (qw.to(torch.float32) / ew[:, None]).to(ctx.dtype)      # == reference's fake-quant W
+            wq = dequant_codes(qw, ew, ctx.dtype)                        # == reference's fake-quant W
             gx = ste_backward_from_mask(g2 @ wq, mx).reshape(ctx.in_shape)
+            del wq
         if ctx.needs_input_grad[1]:
-            xq = (qx.to(torch.float32) / ex[:, None]).to(ctx.dtype)      # == reference's fake-quant x
+            xq = dequant_codes(qx, ex, ctx.dtype)                        # == reference's fake-quant x
             gw = ste_backward_from_mask(g2.t() @ xq, mw)
         return gx, gw, None, None
+
+
+def dequant_codes(codes, row_e, dtype):
+    """out[r, c] = codes[r, c] / row_e[r] in ``dtype`` (exact IEEE quotient, one rounding)."""
+    rows, cols = codes.shape
+    out = torch.empty((rows, cols), dtype=dtype, device=codes.device)
+    with torch.cuda.device(codes.device):
+        rc = _lib.lib().qat_dequant_codes(codes.data_ptr(), row_e.data_ptr(), out.data_ptr(), rows, cols,
+                                          _DTYPES[dtype], _stream_ptr(codes.device))
+    check(rc, "qat_dequant_codes")
+    return out
 
 
 def qlinear_i8(qx, qw, ex, ew, out_dtype):

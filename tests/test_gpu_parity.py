@@ -293,6 +293,23 @@ def test_qlinear_i8_gemm_exact_integer_dot(T, N, K, out_dtype):
     assert err <= tol, (T, N, K, out_dtype, err)
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_dequant_codes_reproduces_forward_output(dtype):
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.utils_quant import dequant_codes, fake_quant_forward
+
+    gen = torch.Generator().manual_seed(21)
+    x = (torch.randn(300, 1024, generator=gen) * 0.6).to(U.DTYPES[dtype]).cuda()
+    for bits in (4, 8):
+        y, c8, _, e, _ = fake_quant_forward(x, bits, False, True, codes_kind=CODES_I8, want_scales=True)
+        back = dequant_codes(c8, e, x.dtype)
+        # identical except -0 (codes carry no sign of zero) and the saturated +-128 codes of bf16 A8
+        sat = (y.float() * e[:, None]).abs() > 127.5
+        same = (back == y) | sat
+        assert bool(same.all()), int((~same).sum())
+        assert int(sat.sum()) <= (0 if dtype == "fp32" else 300)
+
+
 def test_config2_quantize_linear_full_shape():
     """BASELINE config 2: x bf16 [8192, 4096], W bf16 [11008, 4096], W4A8; fused
     path vs the unfused (fake-quant kernels + library GEMM) path, rel <= 1e-2."""
