@@ -395,6 +395,29 @@ def run_b200(args):
             extras["config1_fp32"] = time_config1_fp32(device, max(3, min(K, 20)))
         except Exception as e:
             extras["config1_fp32"] = {"error": f"{type(e).__name__}: {e}"}
+    # ---- BASELINE config 4: full LLaMA-7B W4A8KV4 QAT step with KD loss, data-parallel
+    qat = None
+    if not args.no_qat_step:
+        try:
+            from harness import llama_qat as HQ
+            from harness import qat_bench as QB
+
+            cfg7 = HQ.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4, num_hidden_layers=args.qat_layers)
+            del step, x, w, gx, gw
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+            r = QB.time_qat_step(llm_qat_b200.utils_quant, cfg7, seq=2048, bsz=1, warmup=2,
+                                 steps=max(3, min(K, 5)), device=device, rank=rank, world=world)
+            ms = r["ms_per_step"]
+            if dist is not None:
+                t = torch.tensor([ms], device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            qat = dict(r, ms_per_step=round(ms, 2), tokens_per_s=round(world * 2048 / ms * 1e3), n_gpus=world,
+                       model="LLaMA-7B dims, random init, student W4A8KV4 + frozen FP teacher, KD (KL batchmean), "
+                             "grad checkpointing, AdamW, bf16" + (", DDP/NCCL all-reduce" if world > 1 else ""))
+        except Exception as e:  # keep the headline line even if the big model cannot run
+            qat = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.synchronize()
     clocks = sampler.stop()
 
@@ -420,6 +443,7 @@ def run_b200(args):
         "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     line.update(extras)
+    line["qat_step"] = qat
     print(json.dumps(line), flush=True)
 
 
@@ -489,6 +513,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-qat-step", action="store_true", help="skip the LLaMA-7B QAT-step extra (config 4)")
+    ap.add_argument("--qat-layers", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
