@@ -126,9 +126,9 @@ def test_harness_layer_on_b200_matches_oracle_module(fused, monkeypatch):
     mine = H.DecoderLayer(cfg, llm_qat_b200.utils_quant).bfloat16().cuda()
     mine.load_state_dict(ref_layer.state_dict())
     with torch.no_grad():
-        for p in list(ref_layer.parameters()) + list(mine.parameters()):
+        for p in ref_layer.parameters():
             if p.dim() == 2:
-                p.mul_(0.5 / p.std())            # weights of realistic scale
+                p.normal_(0.0, 0.05)             # keeps the softmax out of its saturated (chaotic) regime
         mine.load_state_dict(ref_layer.state_dict())
     g = torch.Generator().manual_seed(2)
     b, s = 2, 128
