@@ -124,6 +124,18 @@ int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const float* ex, cons
                        void* out, int64_t T, int64_t N, int64_t K, int out_dtype, void* stream);
 
 /*
+ * QuantizeLinear.forward main path in one call (utils_quant.py:197-201,244-250):
+ * qat_sym_fwd (codes-only) on x [T,K] and on w [N,K], then qat_qlinear_i8_fwd.
+ * qx/ex/mx and qw/ew/mw receive the int8 codes, dequant divisors and packed STE
+ * masks (mx / mw may be NULL); reuse_x / reuse_w != 0 skip a quantization whose
+ * outputs the caller still holds.  K % 16 == 0, 2 <= bits <= 8.
+ */
+int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, int8_t* qx, float* ex, uint8_t* mx,
+                          int8_t* qw, float* ew, uint8_t* mw, int64_t T, int64_t N, int64_t K, int dtype,
+                          int a_bits, int w_bits, float clip_lo, float clip_hi, int reuse_x, int reuse_w,
+                          void* stream);
+
+/*
  * Rebuild the fake-quantized tensor from K1's int8 codes and row divisors:
  * out[r,c] = fl(codes[r,c] / row_e[r]) — bit-identical to qat_sym_fwd's y
  * (utils_quant.py:72) wherever the int8 feed did not saturate.  cols % 16 == 0.

@@ -42,6 +42,8 @@ def _declare(lib):
         "qat_qlinear_i8_fwd": (I, [P, P, P, P, P, L, L, L, I, P]),
         # seed, rows, per_row, bf16_operands, dev_counters, stream
         "qat_selftest_fastdiv": (I, [c_uint64, L, I, I, P, P]),
+        # x, w, out, qx, ex, mx, qw, ew, mw, T, N, K, dtype, a_bits, w_bits, lo, hi, reuse_x, reuse_w, stream
+        "qat_qlinear_fused_fwd": (I, [P, P, P, P, P, P, P, P, P, L, L, L, I, I, I, F, F, I, I, P]),
         # codes, row_e, out, rows, cols, dtype, stream
         "qat_dequant_codes": (I, [P, P, P, L, L, I, P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),

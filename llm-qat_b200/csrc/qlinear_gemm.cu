@@ -441,3 +441,27 @@ extern "C" int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const floa
   if (out_dtype == QAT_BF16) return launch<QAT_BF16>(ma, mb, p, st);
   return launch<QAT_F32>(ma, mb, p, st);
 }
+
+// One call for QuantizeLinear.forward's main path (utils_quant.py:197-201,244-250):
+// K1 (codes-only) on the activations, K1 on the weights, then the tcgen05 GEMM.
+// `reuse_x` / `reuse_w` skip a quantization whose outputs the caller still holds
+// (q/k/v share one input; weights only change at optimizer steps).
+extern "C" int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, int8_t* qx, float* ex,
+                                     uint8_t* mx, int8_t* qw, float* ew, uint8_t* mw, int64_t T, int64_t N,
+                                     int64_t K, int dtype, int a_bits, int w_bits, float clip_lo,
+                                     float clip_hi, int reuse_x, int reuse_w, void* stream) {
+  using namespace qat;
+  QAT_CHECK_ARG(qx && ex && qw && ew, "code / scale buffers must be provided");
+  QAT_CHECK_ARG(a_bits >= 2 && a_bits <= 8 && w_bits >= 2 && w_bits <= 8, "int8 grid needs 2 <= bits <= 8");
+  if (!reuse_x) {
+    int rc = qat_sym_fwd(x, nullptr, qx, QAT_CODES_I8, nullptr, ex, mx, clip_lo, clip_hi, T, K, dtype, a_bits,
+                         nullptr, 0, stream);
+    if (rc != QAT_OK) return rc;
+  }
+  if (!reuse_w) {
+    int rc = qat_sym_fwd(w, nullptr, qw, QAT_CODES_I8, nullptr, ew, mw, clip_lo, clip_hi, N, K, dtype, w_bits,
+                         nullptr, 0, stream);
+    if (rc != QAT_OK) return rc;
+  }
+  return qat_qlinear_i8_fwd(qx, qw, ex, ew, out, T, N, K, dtype, stream);
+}

@@ -17,6 +17,8 @@ Install under the reference's import name before its model file is imported::
     from models.modeling_llama_quant import LlamaForCausalLM
 
 Run-time knobs (environment; signatures stay the reference's):
+  QAT_B200_CACHE=0|1          memoise weight codes per module (until the parameter changes) and the
+                              last activation's codes per device (default 1).
   QAT_B200_FUSED_LINEAR=0|1   QuantizeLinear uses the integer-grid tcgen05 GEMM (default 1, taken
                               when shapes/dtypes allow) or the fake-quant kernels + F.linear (0).
 """
@@ -227,12 +229,42 @@ def _fused_linear_enabled() -> bool:
     return os.environ.get("QAT_B200_FUSED_LINEAR", "1") != "0"
 
 
+def _cache_enabled() -> bool:
+    return os.environ.get("QAT_B200_CACHE", "1") != "0"
+
+
+def _feed_layout(rows: int, cols: int):
+    """Byte offsets of (codes int8 [rows, cols], divisors f32 [rows], packed mask) in one blob."""
+    n = rows * cols
+    off_e = (n + 255) & ~255
+    off_m = off_e + ((rows * 4 + 255) & ~255)
+    return off_e, off_m, off_m + (n + 7) // 8
+
+
+def _feed_views(blob: torch.Tensor, rows: int, cols: int):
+    off_e, off_m, total = _feed_layout(rows, cols)
+    codes = blob[: rows * cols].view(torch.int8).view(rows, cols)
+    e = blob[off_e: off_e + rows * 4].view(torch.float32)
+    mask = blob[off_m: total]
+    return codes, e, mask
+
+
+# Single-slot memo of the last quantized activation per device: q/k/v (and gate/up)
+# receive the very same tensor, so its codes are produced once (SURVEY.md 8f-2).
+# The slot holds a reference to the input, so its storage cannot be recycled
+# while the key (data_ptr, version, ...) is live.
+_ACT_SLOT: dict = {}
+
+
 class _QuantLinearFn(torch.autograd.Function):
     """QuantizeLinear main path (3 <= w_bits <= 8, 3 <= a_bits <= 8, symmetric,
     per-row scales) on the integer grid — reference utils_quant.py:197-201,244-250.
 
-    forward : K1 codes-only passes (int8 codes + row divisors + packed STE masks)
-              -> tcgen05 int8 GEMM with the dual-scale epilogue (K4).
+    forward : ONE C call: K1 codes-only passes (int8 codes + row divisors + packed
+              STE masks) -> tcgen05 int8 GEMM with the dual-scale epilogue (K4).
+              The weight's codes are memoised on the module, keyed on the
+              parameter's (data_ptr, _version): they are rebuilt only after an
+              optimizer step, not on every forward / checkpoint recompute.
     backward: dequantized operands are rebuilt from codes (q / e, bit-identical
               to the reference's fake-quant outputs); dgrad/wgrad are plain
               library GEMMs; the STE masks saved by the forward gate them.
@@ -241,36 +273,73 @@ class _QuantLinearFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, input, weight, w_bits, a_bits):
-        lead = input.shape[:-1]
+    def forward(ctx, input, weight, w_bits, a_bits, owner):
         K = input.shape[-1]
         N = weight.shape[0]
-        x2 = input.reshape(-1, K)
-        clip = (-2.0, 2.0)  # utils_quant.py:198,245
-        _, qx, _, ex, mx = fake_quant_forward(x2, a_bits, False, True, want_y=False, codes_kind=CODES_I8,
-                                              want_scales=True, mask_clip=clip)
-        _, qw, _, ew, mw = fake_quant_forward(weight, w_bits, False, True, want_y=False, codes_kind=CODES_I8,
-                                              want_scales=True, mask_clip=clip)
-        out = qlinear_i8(qx, qw, ex, ew, input.dtype)
-        ctx.save_for_backward(qx, qw, ex, ew, mx, mw)
+        x2 = input.detach()
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        T = x2.numel() // K
+        dev = x2.device
+        dt = _DTYPES[x2.dtype]
+        stream = _stream_ptr(dev)
+        use_cache = _cache_enabled()
+
+        xkey = (x2.data_ptr(), x2._version, T, K, dt, a_bits, stream)
+        slot = _ACT_SLOT.get(dev.index) if use_cache else None
+        if slot is not None and slot[0] == xkey:
+            xblob, reuse_x = slot[2], 1
+        else:
+            xblob, reuse_x = torch.empty(_feed_layout(T, K)[2], dtype=torch.uint8, device=dev), 0
+        wkey = (w.data_ptr(), weight._version, N, K, dt, w_bits, stream)
+        cached = getattr(owner, "_qat_wfeed", None) if (use_cache and owner is not None) else None
+        if cached is not None and cached[0] == wkey:
+            wblob, reuse_w = cached[1], 1
+        else:
+            wblob, reuse_w = torch.empty(_feed_layout(N, K)[2], dtype=torch.uint8, device=dev), 0
+
+        out = torch.empty((T, N), dtype=x2.dtype, device=dev)
+        xe, xm, _ = _feed_layout(T, K)
+        we, wm, _ = _feed_layout(N, K)
+        xb, wb = xblob.data_ptr(), wblob.data_ptr()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().qat_qlinear_fused_fwd(
+                x2.data_ptr(), w.data_ptr(), out.data_ptr(), xb, xb + xe, xb + xm, wb, wb + we, wb + wm,
+                T, N, K, dt, int(a_bits), int(w_bits), -2.0, 2.0,  # clip: utils_quant.py:198,245
+                reuse_x, reuse_w, stream)
+        check(rc, "qat_qlinear_fused_fwd")
+        if use_cache:
+            _ACT_SLOT[dev.index] = (xkey, x2, xblob)
+            if owner is not None:
+                owner._qat_wfeed = (wkey, wblob)
+        ctx.save_for_backward(xblob, wblob)
+        ctx.dims = (T, N, K)
         ctx.in_shape = input.shape
         ctx.dtype = input.dtype
-        return out.reshape(*lead, N)
+        return out.view(*input.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, grad_output):
-        qx, qw, ex, ew, mx, mw = ctx.saved_tensors
-        g2 = grad_output.reshape(-1, grad_output.shape[-1])
+        xblob, wblob = ctx.saved_tensors
+        T, N, K = ctx.dims
+        g2 = grad_output.reshape(T, N)
         g2 = g2 if g2.is_contiguous() else g2.contiguous()
         gx = gw = None
         if ctx.needs_input_grad[0]:
+            qw, ew, _ = _feed_views(wblob, N, K)
+            _, _, mx = _feed_views(xblob, T, K)
             wq = dequant_codes(qw, ew, ctx.dtype)                        # == reference's fake-quant W
-            gx = ste_backward_from_mask(g2 @ wq, mx).reshape(ctx.in_shape)
+            gx = ste_backward_from_mask(g2 @ wq, mx).view(ctx.in_shape)
             del wq
         if ctx.needs_input_grad[1]:
+            qx, ex, _ = _feed_views(xblob, T, K)
+            _, _, mw = _feed_views(wblob, N, K)
             xq = dequant_codes(qx, ex, ctx.dtype)                        # == reference's fake-quant x
             gw = ste_backward_from_mask(g2.t() @ xq, mw)
-        return gx, gw, None, None
+        return gx, gw, None, None, None
 
 
 def dequant_codes(codes, row_e, dtype):
@@ -341,7 +410,7 @@ class QuantizeLinear(nn.Linear):
         real_weights = self.weight
 
         if self._can_fuse(input_):
-            return _QuantLinearFn.apply(input_, real_weights, self.w_bits, self.a_bits)
+            return _QuantLinearFn.apply(input_, real_weights, self.w_bits, self.a_bits, self)
 
         if self.w_bits >= 32:
             weight = self.weight

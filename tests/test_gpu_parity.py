@@ -293,6 +293,47 @@ def test_qlinear_i8_gemm_exact_integer_dot(T, N, K, out_dtype):
     assert err <= tol, (T, N, K, out_dtype, err)
 
 
+def test_quantize_linear_caches_are_transparent(monkeypatch):
+    """Weight codes are memoised per module until the parameter changes; the last
+    activation's codes are shared by consecutive layers fed the same tensor (q/k/v).
+    Neither may change a result."""
+    from llm_qat_b200 import QuantizeLinear
+
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(4, 50, 256, generator=gen).bfloat16().cuda()
+    go = torch.randn(4, 50, 384, generator=gen).bfloat16().cuda()
+    ws = [(torch.randn(384, 256, generator=gen) * 0.05).bfloat16().cuda() for _ in range(3)]
+
+    def run(cache):
+        monkeypatch.setenv("QAT_B200_CACHE", cache)
+        monkeypatch.setenv("QAT_B200_FUSED_LINEAR", "1")
+        lins = [QuantizeLinear(256, 384, w_bits=4, a_bits=8).bfloat16().cuda() for _ in range(3)]
+        res = []
+        for lin, w in zip(lins, ws):
+            with torch.no_grad():
+                lin.weight.copy_(w)
+        xi = x.clone().requires_grad_(True)
+        outs = [lin(xi) for lin in lins]              # same input three times (q/k/v pattern)
+        sum(o.float().mul(go.float()).sum() for o in outs).backward()
+        res += [o.detach().clone() for o in outs] + [xi.grad.clone()] + [lin.weight.grad.clone() for lin in lins]
+        # optimizer-style in-place update: the cached codes must be dropped
+        with torch.no_grad():
+            lins[0].weight.mul_(-1.5)
+        res.append(lins[0](xi).detach().clone())
+        res.append(lins[0](xi).detach().clone())       # second call hits the weight cache
+        # in-place change of the activation: the activation slot must miss
+        with torch.no_grad():
+            xi.mul_(0.5)
+        res.append(lins[1](xi).detach().clone())
+        return res
+
+    a, b = run("1"), run("0")
+    assert len(a) == len(b)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(u, v), i
+    assert torch.equal(a[7], a[8]) and not torch.equal(a[0], a[7])
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_dequant_codes_reproduces_forward_output(dtype):
     from llm_qat_b200._lib import CODES_I8
