@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""GPU-box tool: where does a LLaMA-7B decoder layer's fwd+bwd time go?
+torch.profiler kernel table for the product (fused) and the reference eager path."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from torch.profiler import profile, ProfilerActivity
+from harness import llama_qat as H
+from oracle import ref_module as R
+import llm_qat_b200
+
+cfg = H.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4)
+seq, bsz = 2048, 1
+for name, quant in (("b200_fused", llm_qat_b200.utils_quant), ("reference_eager", R)):
+    torch.manual_seed(0)
+    layer = H.DecoderLayer(cfg, quant).bfloat16().cuda()
+    x = torch.randn(bsz, seq, cfg.hidden_size).bfloat16().cuda().requires_grad_(True)
+    go = torch.randn(bsz, seq, cfg.hidden_size).bfloat16().cuda()
+    mask = H.causal_mask(bsz, seq, torch.bfloat16, "cuda")
+    pos = torch.arange(seq, device="cuda")[None].expand(bsz, seq)
+    def step():
+        y = layer(x, mask, pos); y.backward(go); x.grad = None
+        for p in layer.parameters(): p.grad = None
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(10): step()
+    t_cpu = (time.perf_counter() - t0) / 10 * 1e3
+    torch.cuda.synchronize()
+    t_all = (time.perf_counter() - t0) / 10 * 1e3
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(3): step()
+        torch.cuda.synchronize()
+    print(f"==== {name}: cpu-enqueue {t_cpu:.2f} ms/step, wall {t_all:.2f} ms/step")
+    evs = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == 'CUDA'] if hasattr(prof.key_averages()[0], 'device_type') else prof.key_averages()
+    rows = sorted(prof.key_averages(), key=lambda e: -getattr(e, 'self_device_time_total', 0))[:22]
+    tot = sum(getattr(e, 'self_device_time_total', 0) for e in prof.key_averages())
+    print(f"total device time per step: {tot/3/1e3:.2f} ms")
+    for e in rows:
+        print(f"{getattr(e,'self_device_time_total',0)/3/1e3:8.3f} ms  x{e.count//3:4d}  {e.key[:90]}")

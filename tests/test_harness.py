@@ -143,6 +143,12 @@ def test_harness_layer_on_b200_matches_oracle_module(fused, monkeypatch):
         y.backward(go)
         outs.append((y.float(), x.grad.float(), layer.mlp.down_proj.weight.grad.float(),
                      layer.self_attn.q_proj.weight.grad.float()))
+    # unfused: bit-identical quantizers + the same library GEMM => only bf16 accumulation noise.
+    # fused: the integer-grid GEMM is exact while the reference rounds each dequantized operand
+    # to bf16 first, a ~3e-3 relative difference per linear; the 4-bit K/V and next-layer
+    # quantizers turn that into code flips for ~0.6 % of elements (one 4-bit step each), i.e. a
+    # few 1e-2 after a whole layer.  Single-linear parity is asserted at 1e-2 in test_gpu_parity.
+    tol = 1e-2 if fused == "0" else 8e-2
     for name, a, c in zip(("out", "dx", "dW_down", "dW_q"), outs[0], outs[1]):
         rel = ((a - c).norm() / a.norm()).item()
-        assert rel < 3e-2, (name, rel, fused)
+        assert rel < tol, (name, rel, fused)
