@@ -123,6 +123,11 @@ int qat_lowbit_weight_fwd(const void* w, void* w_eff, int64_t rows, int64_t cols
 int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const float* ex, const float* ew,
                        void* out, int64_t T, int64_t N, int64_t K, int out_dtype, void* stream);
 
+/* Tuning knob of the contraction: CTAs per tcgen05.mma.  2 = CTA pairs on 256x256
+ * tiles (cta_group::2), 1 = single CTAs on 128x256 tiles, 0 = choose per problem
+ * (the default; also settable once through the environment, QAT_B200_GEMM_CG). */
+int qat_set_gemm_cta_group(int cta_group);
+
 /*
  * QuantizeLinear.forward main path in one call (utils_quant.py:197-201,244-250):
  * qat_sym_fwd (codes-only) on x [T,K] and on w [N,K], then qat_qlinear_i8_fwd.

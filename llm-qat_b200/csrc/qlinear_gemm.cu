@@ -7,20 +7,34 @@
 // emits in its codes-only mode.  The integer dot product is exact (s32
 // accumulators), so the result is at least as accurate as the reference's.
 //
-// sm_100a design
-//   * persistent grid, one CTA per SM, static round-robin over 128x256 tiles;
-//   * warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4 stages)
-//   * warp 1   : MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::i8,
-//                               M128 x N256 x K32, s32 accumulators in TMEM)
+// sm_100a design (template parameter CG = CTAs per MMA, the PTX cta_group)
+//   * persistent grid, one CTA per SM, static round-robin over output tiles;
+//   * CG == 2 (default for large problems): the two CTAs of a cluster (one TPC)
+//     own one 256x256 tile.  Each CTA stages its own 128 rows of A and its own
+//     128-row half of B (32 KB per k-block instead of 48 KB) and holds 128 rows
+//     of the accumulator in its TMEM; the leader CTA issues
+//     tcgen05.mma.cta_group::2 (M256 x N256 x K32), which reads B from both
+//     CTAs' shared memory.  Per SM the operand read rate drops from 96 to
+//     64 B/clk — below the 128 B/clk shared-memory port — which is what lets the
+//     tensor pipe stay busy (the CG == 1 kernel measured 75 % tensor-active).
+//   * CG == 1: one CTA per 128x256 tile (small problems, odd SM counts).
+//   * warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle; with
+//                               CG == 2 both CTAs' loads complete on the
+//                               leader's mbarrier)
+//   * warp 1   : MMA issuer    (one thread of the leader CTA, kind::i8, s32
+//                               accumulators in TMEM; tcgen05.commit multicasts
+//                               "stage free" / "accumulator full" to both CTAs)
 //   * warp 2   : TMEM allocator (512 columns = 2 accumulator stages)
 //   * warps 4-7: epilogue      (tcgen05.ld 32x32b.x32 -> I2F -> x row/col
 //                               scales -> bf16/fp32 -> 16-byte global stores),
 //                               overlapped with the next tile's MMAs.
-//   * smem: 4 x (16 KB A + 32 KB B) + column-scale staging = ~195 KB.
+//   * smem: CG1 4 x (16 KB A + 32 KB B), CG2 6 x (16 KB A + 16 KB B), plus
+//     column-scale staging = ~195 KB.
 // Tensor-bound: 2*T*N*K integer ops; see DESIGN.md "K4".
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include <mutex>
 
@@ -29,23 +43,27 @@
 namespace qat {
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
+constexpr int BLOCK_M = 128;  // accumulator rows per CTA (TMEM lanes)
+constexpr int BLOCK_N = 256;  // accumulator columns per tile
 constexpr int BLOCK_K = 128;  // bytes == int8 elements: one 128B swizzle row
 constexpr int UMMA_K = 32;    // elements per tcgen05.mma.kind::i8
-constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;  // warps 4..7; (warp % 4) selects the TMEM lane quadrant
 constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = kEpiThreads / 32;
 
-constexpr uint32_t kABytes = BLOCK_M * BLOCK_K;  // 16 KB
-constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K;  // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
-
-struct SmemLayout {
-  // offsets from the 1024-byte aligned base
+// Per-CTA shared-memory plan.  CG CTAs cooperate on one (CG*128) x 256 tile.
+template <int CG>
+struct Cfg {
+  static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr int kTileM = BLOCK_M * CG;                    // output rows per tile
+  static constexpr int kBRows = BLOCK_N / CG;                    // B rows staged by each CTA
+  static constexpr uint32_t kABytes = BLOCK_M * BLOCK_K;         // 16 KB
+  static constexpr uint32_t kBBytes = kBRows * BLOCK_K;          // 32 KB | 16 KB
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  // offsets from the 1024-byte aligned base (identical in both CTAs of a pair)
   static __host__ __device__ constexpr uint32_t a(int s) { return (uint32_t)s * kStageBytes; }
   static __host__ __device__ constexpr uint32_t b(int s) { return (uint32_t)s * kStageBytes + kABytes; }
   static constexpr uint32_t colscale = kStages * kStageBytes;             // 2 x 256 floats
@@ -56,8 +74,9 @@ struct SmemLayout {
   static __host__ __device__ constexpr uint32_t tempty(int a) { return bars + 8u * (2 * kStages + kAccStages + a); }
   static constexpr uint32_t tmem_ptr = bars + 8u * (2 * kStages + 2 * kAccStages);
   static constexpr uint32_t total = tmem_ptr + 16;
+  static constexpr uint32_t kSmemBytes = total + 1024;  // slack for manual 1024B alignment
 };
-constexpr uint32_t kSmemBytes = SmemLayout::total + 1024;  // slack for manual 1024B alignment
+static_assert(Cfg<1>::kSmemBytes <= 232448 && Cfg<2>::kSmemBytes <= 232448, "over the 227 KB per-CTA limit");
 
 // ---- PTX wrappers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -104,6 +123,34 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// CG == 2: executed by both CTAs of the pair; the mbarrier operand has the
+// peer bit (24) of its shared::cluster address cleared, so the transaction
+// bytes land on the LEADER CTA's barrier wherever the data lands.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                 int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -114,15 +161,32 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// arrives (once the MMAs issued so far retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> s32
+template <int CG>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -207,14 +271,21 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, int64_t row, in
   }
 }
 
-template <int OUT_DT>
+template <int OUT_DT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const GemmParams p) {
+  using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
+  // the dynamic window starts at the same shared::cta offset in every CTA of the
+  // kernel, so `base` — and with it every barrier / tile offset — is identical
+  // in both CTAs of a pair (the multicast commit and the peer-bit trick need it)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // CTA (pair) index
+  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_tiles = p.m_blocks * p.n_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -223,43 +294,57 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(base + SmemLayout::full(s), 1);
-      mbar_init(base + SmemLayout::empty(s), 1);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(base + C::full(s), 1);    // the leader's producer: arrive.expect_tx (bytes of both CTAs)
+      mbar_init(base + C::empty(s), 1);   // one tcgen05.commit arrival (multicast to both CTAs when CG == 2)
     }
 #pragma unroll
     for (int a = 0; a < kAccStages; ++a) {
-      mbar_init(base + SmemLayout::tfull(a), 1);
-      mbar_init(base + SmemLayout::tempty(a), kEpiThreads);
+      mbar_init(base + C::tfull(a), 1);
+      mbar_init(base + C::tempty(a), CG * kEpiWarps);   // one arrival per epilogue warp of every CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     base + SmemLayout::tmem_ptr),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + C::tmem_ptr),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + C::tmem_ptr),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // peers touch our barriers: cluster-wide
   tcgen05_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + SmemLayout::tmem_ptr);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + C::tmem_ptr);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own rows) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
+        const int32_t a_row = m_blk * C::kTileM + (int)rank * BLOCK_M;
+        const int32_t b_row = n_blk * BLOCK_N + (int)rank * C::kBRows;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(base + SmemLayout::empty(stage), phase ^ 1u);
-          const uint32_t full = base + SmemLayout::full(stage);
-          mbar_expect_tx(full, kStageBytes);
-          tma_load_2d(base + SmemLayout::a(stage), &map_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(base + SmemLayout::b(stage), &map_b, full, kb * BLOCK_K, n_blk * BLOCK_N);
-          if (++stage == kStages) {
+          mbar_wait(base + C::empty(stage), phase ^ 1u);   // own copy: the commit is multicast
+          const uint32_t full = base + C::full(stage);
+          if (CG == 1) {
+            mbar_expect_tx(full, C::kStageBytes);
+            tma_load_2d(base + C::a(stage), &map_a, full, kb * BLOCK_K, a_row);
+            tma_load_2d(base + C::b(stage), &map_b, full, kb * BLOCK_K, b_row);
+          } else {
+            if (rank == 0) mbar_expect_tx(full, 2 * C::kStageBytes);
+            tma_load_2d_pair(base + C::a(stage), &map_a, full, kb * BLOCK_K, a_row);
+            tma_load_2d_pair(base + C::b(stage), &map_b, full, kb * BLOCK_K, b_row);
+          }
+          if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -267,33 +352,35 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_i8(BLOCK_M, BLOCK_N);
+    // ===================== MMA issuer (single thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(C::kTileM, BLOCK_N);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(base + SmemLayout::tempty(acc), acc_phase ^ 1u);  // epilogue drained this stage
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        mbar_wait(base + C::tempty(acc), acc_phase ^ 1u);  // every epilogue warp drained this stage
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(base + SmemLayout::full(stage), phase);
+          mbar_wait(base + C::full(stage), phase);
           tcgen05_fence_after();
-          const uint64_t adesc = make_smem_desc(base + SmemLayout::a(stage));
-          const uint64_t bdesc = make_smem_desc(base + SmemLayout::b(stage));
+          const uint64_t adesc = make_smem_desc(base + C::a(stage));
+          const uint64_t bdesc = make_smem_desc(base + C::b(stage));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes inside the 128B swizzle atom: +2 in the (>>4) address field
-            umma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+            umma_i8<CG>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(base + SmemLayout::empty(stage));  // frees the smem stage when the MMAs retire
-          if (++stage == kStages) {
+          // frees the smem stage (in both CTAs) when the MMAs retire
+          if (CG == 1) umma_commit(base + C::empty(stage)); else umma_commit_pair(base + C::empty(stage));
+          if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(base + SmemLayout::tfull(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 1) umma_commit(base + C::tfull(acc)); else umma_commit_pair(base + C::tfull(acc));
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
@@ -301,17 +388,17 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue (4 warps, 128 threads) =====================
+    // ===================== epilogue (4 warps, 128 threads, own 128 accumulator rows) =====================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
     const bool vec_ok = (OUT_DT == QAT_BF16) ? (p.N % 8 == 0) : (p.N % 4 == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
-      const int64_t row = (int64_t)m_blk * BLOCK_M + quad * 32 + lane;
+      const int64_t row = (int64_t)m_blk * C::kTileM + (int64_t)rank * BLOCK_M + quad * 32 + lane;
       const int64_t col_base = (int64_t)n_blk * BLOCK_N;
-      float* colscale = reinterpret_cast<float*>(base_ptr + SmemLayout::colscale) + acc * BLOCK_N;
+      float* colscale = reinterpret_cast<float*>(base_ptr + C::colscale) + acc * BLOCK_N;
       // stage 1/ew for this tile's 256 columns (2 per thread) while the MMAs run
 #pragma unroll
       for (int j = et; j < BLOCK_N; j += kEpiThreads) {
@@ -320,7 +407,7 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       const float row_scale = (row < p.T) ? __frcp_rn(p.ex[row]) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // colscale visible to the 4 warps
-      mbar_wait(base + SmemLayout::tfull(acc), acc_phase);
+      mbar_wait(base + C::tfull(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
@@ -332,7 +419,10 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           store_chunk<OUT_DT>(p, row, col_base + c * 32, r, row_scale, colscale + c * 32, vec_ok);
       }
       tcgen05_fence_before();
-      mbar_arrive(base + SmemLayout::tempty(acc));
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(base + C::tempty(acc)); else mbar_arrive_remote(base + C::tempty(acc), 0u);
+      }
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1u;
@@ -341,11 +431,15 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody leaves while its peer may still use it
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
-                 : "memory");
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+                   : "memory");
   }
 }
 
@@ -390,25 +484,60 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box
   return QAT_OK;
 }
 
-template <int OUT_DT>
+template <int OUT_DT, int CG>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<CG>;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qlinear_i8_kernel<OUT_DT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(qlinear_i8_kernel<OUT_DT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qlinear_i8_kernel)");
     attr_set = true;
   }
   const int tiles = p.m_blocks * p.n_blocks;
-  int grid = num_sms();
-  if (grid > tiles) grid = tiles;
-  qlinear_i8_kernel<OUT_DT><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, p);
+  int units = num_sms() / CG;   // one CTA (pair) per SM (TPC)
+  if (units > tiles) units = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, qlinear_i8_kernel<OUT_DT, CG>, ma, mb, p);
+  if (e != cudaSuccess) return cuda_fail(e, "qlinear_i8_kernel launch");
   QAT_CHECK_LAUNCH("qlinear_i8_kernel");
   return QAT_OK;
 }
 
+// CTAs per MMA for a problem: pairs pay off once there are enough 256-row tiles
+// to fill the machine; QAT_B200_GEMM_CG=1|2 forces a choice (tests, profiling).
+int g_forced_cg = -1;  // -1: not yet read from the environment; 0: automatic
+int pick_cta_group(int64_t T, int64_t N) {
+  if (g_forced_cg < 0) {
+    const char* v = getenv("QAT_B200_GEMM_CG");
+    g_forced_cg = (v && (v[0] == '1' || v[0] == '2')) ? v[0] - '0' : 0;
+  }
+  if (g_forced_cg) return g_forced_cg;
+  if (num_sms() % 2) return 1;
+  const int64_t pair_tiles = ((T + 255) / 256) * ((N + BLOCK_N - 1) / BLOCK_N);
+  return pair_tiles >= num_sms() / 2 ? 2 : 1;
+}
+
 }  // namespace
 }  // namespace qat
+
+extern "C" int qat_set_gemm_cta_group(int cta_group) {
+  using namespace qat;
+  QAT_CHECK_ARG(cta_group == 0 || cta_group == 1 || cta_group == 2, "cta_group must be 0 (automatic), 1 or 2");
+  g_forced_cg = cta_group;
+  return QAT_OK;
+}
 
 extern "C" int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const float* ex, const float* ew,
                                   void* out, int64_t T, int64_t N, int64_t K, int out_dtype, void* stream) {
@@ -422,10 +551,11 @@ extern "C" int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const floa
   QAT_CHECK_ARG(((uintptr_t)qx & 15) == 0 && ((uintptr_t)qw & 15) == 0, "code pointers must be 16-byte aligned");
   QAT_CHECK_ARG(((uintptr_t)out & 15) == 0, "out must be 16-byte aligned");
   QAT_CHECK_ARG(T < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension too large");
+  const int cg = pick_cta_group(T, N);
   CUtensorMap ma, mb;
   int rc = make_map(&ma, qx, T, K, BLOCK_M);
   if (rc != QAT_OK) return rc;
-  rc = make_map(&mb, qw, N, K, BLOCK_N);
+  rc = make_map(&mb, qw, N, K, BLOCK_N / cg);
   if (rc != QAT_OK) return rc;
   GemmParams p{};
   p.ex = ex;
@@ -434,12 +564,12 @@ extern "C" int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const floa
   p.T = T;
   p.N = N;
   p.K = K;
-  p.m_blocks = (int)((T + BLOCK_M - 1) / BLOCK_M);
+  p.m_blocks = (int)((T + BLOCK_M * cg - 1) / (BLOCK_M * cg));
   p.n_blocks = (int)((N + BLOCK_N - 1) / BLOCK_N);
   p.k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (out_dtype == QAT_BF16) return launch<QAT_BF16>(ma, mb, p, st);
-  return launch<QAT_F32>(ma, mb, p, st);
+  if (cg == 2) return out_dtype == QAT_BF16 ? launch<QAT_BF16, 2>(ma, mb, p, st) : launch<QAT_F32, 2>(ma, mb, p, st);
+  return out_dtype == QAT_BF16 ? launch<QAT_BF16, 1>(ma, mb, p, st) : launch<QAT_F32, 1>(ma, mb, p, st);
 }
 
 // One call for QuantizeLinear.forward's main path (utils_quant.py:197-201,244-250):

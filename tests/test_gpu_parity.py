@@ -272,12 +272,25 @@ def test_lowbit_weight_vs_reference_goldens(dtype):
 
 # --------------------------------------------------------------- K4: tcgen05 GEMM
 @pytest.mark.parametrize("T,N,K", [(128, 256, 128), (256, 512, 4096), (200, 264, 1040), (8, 80, 192),
-                                   (1024, 11008, 4096)])
+                                   (1024, 11008, 4096), (300, 520, 2064), (2048, 4096, 11008)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
-def test_qlinear_i8_gemm_exact_integer_dot(T, N, K, out_dtype):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_qlinear_i8_gemm_exact_integer_dot(T, N, K, out_dtype, cta_group):
     """int8 x int8 -> s32 is exact, so the only rounding is the epilogue's:
-    compare with an int64 reference scaled in float64."""
+    compare with an int64 reference scaled in float64.  Both tile plans (single
+    CTAs on 128x256 tiles, CTA pairs on 256x256 tiles) on every shape, ragged
+    ones included (rows/columns/K beyond the edge are TMA zero fill)."""
+    from llm_qat_b200 import _lib
     from llm_qat_b200.utils_quant import qlinear_i8
+
+    _lib.check(_lib.lib().qat_set_gemm_cta_group(cta_group))
+    try:
+        _qlinear_exact_case(qlinear_i8, T, N, K, out_dtype)
+    finally:
+        _lib.lib().qat_set_gemm_cta_group(0)
+
+
+def _qlinear_exact_case(qlinear_i8, T, N, K, out_dtype):
 
     gen = torch.Generator().manual_seed(T + N + K)
     qx = torch.randint(-127, 128, (T, K), generator=gen, dtype=torch.int8)
