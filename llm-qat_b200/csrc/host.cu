@@ -4,10 +4,15 @@
 // (SymQuantizer.apply / .backward, utils_quant.py:37-87): copy in, run, copy out.
 //
 // Rows are independent, so the tensor is cut into row chunks that flow through
-// a three-stage pipeline on three streams — H2D(x, g) | K1/K2 + K3 | D2H(y, gx)
-// — overlapping both PCIe directions with the kernels.  Everything is ordered
+// a three-stage pipeline — H2D(x, g) | K1/K2 + K3 | D2H(y, gx) — overlapping
+// both PCIe directions with the kernels.  One stream per direction: measured on
+// the B200 box, two concurrent copies in the SAME direction (x beside g) drop the
+// link from 41 to 33 GB/s per direction, so kStreamsPerDirection stays 1.  The
+// ceiling is the link itself: 47 GB/s per direction with both directions busy
+// (tests/gpu_pcie_probe.py), 41 GB/s at this pipeline's 8 MB copy size.  Everything is ordered
 // after prior work on the caller's stream and the caller's stream waits for the
 // last D2H, so stream semantics are those of a single asynchronous call.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -16,7 +21,7 @@ namespace qat {
 namespace {
 
 struct Pipe {
-  cudaStream_t in = nullptr, out = nullptr;
+  cudaStream_t in[2] = {nullptr, nullptr}, out[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> ev;
   int device = -1;
   cudaEvent_t event(size_t i) {
@@ -39,13 +44,23 @@ Pipe* get_pipe() {
     if (p.device == dev) return &p;
   Pipe p;
   p.device = dev;
-  if (cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-  if (cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaStreamCreateWithFlags(&p.in[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&p.out[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  }
   pipes.push_back(p);
   return &pipes.back();
 }
 
-constexpr int64_t kTargetChunkBytes = 8ll << 20;  // per tensor per chunk
+// per tensor per chunk; QAT_B200_HOST_CHUNK_MB=1..64 overrides (tuning)
+int64_t target_chunk_bytes() {
+  static const int64_t v = [] {
+    const char* e = getenv("QAT_B200_HOST_CHUNK_MB");
+    const int mb = e ? atoi(e) : 0;
+    return (int64_t)((mb >= 1 && mb <= 64) ? mb : 8) << 20;
+  }();
+  return v;
+}
 
 template <bool SYM>
 int fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_host, float lo,
@@ -80,11 +95,37 @@ int fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_
   char* dg = dy + tensor_bytes;
   char* dgx = dg + tensor_bytes;
 
-  int64_t chunk_rows = kTargetChunkBytes / (row_bytes > 0 ? row_bytes : 1);
+  // Chunk schedule: steady-state chunks of ~8 MB per tensor (smaller ones are
+  // bound by the host's enqueue rate), but the first and last chunks ramp
+  // 1/8, 1/4, 1/2 of that: the D2H direction idles while the first chunk goes
+  // in, and the H2D direction while the last one comes out, so short end
+  // chunks cut those two bubbles from ~0.3 ms to ~0.04 ms per call.
+  int64_t chunk_rows = target_chunk_bytes() / (row_bytes > 0 ? row_bytes : 1);
   if (chunk_rows < 1) chunk_rows = 1;
   // keep chunk starts 16-byte aligned for any row pitch
-  while ((chunk_rows * row_bytes) % 16 != 0) ++chunk_rows;
-  const int64_t nchunks = (rows + chunk_rows - 1) / chunk_rows;
+  int64_t align_rows = 1;
+  while ((align_rows * row_bytes) % 16 != 0) ++align_rows;
+  auto round_rows = [&](int64_t r) { return ((r < 1 ? 1 : r) + align_rows - 1) / align_rows * align_rows; };
+  chunk_rows = round_rows(chunk_rows);
+  std::vector<int64_t> bounds;  // chunk c covers rows [bounds[c], bounds[c+1])
+  {
+    const int64_t ramp[3] = {round_rows(chunk_rows / 8), round_rows(chunk_rows / 4), round_rows(chunk_rows / 2)};
+    const int64_t ramp_total = ramp[0] + ramp[1] + ramp[2];
+    bounds.push_back(0);
+    if (rows >= 2 * ramp_total + chunk_rows) {
+      int64_t r = 0;
+      for (int i = 0; i < 3; ++i) bounds.push_back(r += ramp[i]);
+      const int64_t steady_end = rows - ramp_total;
+      while (steady_end - r > chunk_rows + chunk_rows / 2) bounds.push_back(r += chunk_rows);
+      if (steady_end > r) bounds.push_back(r = steady_end);
+      for (int i = 2; i >= 1; --i) bounds.push_back(r += ramp[i]);
+      bounds.push_back(rows);
+    } else {
+      for (int64_t r = chunk_rows; r < rows; r += chunk_rows) bounds.push_back(r);
+      bounds.push_back(rows);
+    }
+  }
+  const int64_t nchunks = (int64_t)bounds.size() - 1;
 
   cudaError_t e;
 #define QAT_TRY(call)                                  \
@@ -93,25 +134,30 @@ int fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_
     if (e != cudaSuccess) return cuda_fail(e, #call);  \
   } while (0)
 
+  const int lanes = bwd ? 2 : 1;  // lane 0: x -> y, lane 1: g -> gx
+  constexpr int kStreamsPerDirection = 1;
   cudaEvent_t ev_start = pipe->event(0);
   if (ev_start == nullptr) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
   QAT_TRY(cudaEventRecord(ev_start, st));
-  QAT_TRY(cudaStreamWaitEvent(pipe->in, ev_start, 0));
-  QAT_TRY(cudaStreamWaitEvent(pipe->out, ev_start, 0));
+  for (int l = 0; l < lanes; ++l) {
+    QAT_TRY(cudaStreamWaitEvent(pipe->in[l % kStreamsPerDirection], ev_start, 0));
+    QAT_TRY(cudaStreamWaitEvent(pipe->out[l % kStreamsPerDirection], ev_start, 0));
+  }
 
   for (int64_t c = 0; c < nchunks; ++c) {
-    const int64_t r0 = c * chunk_rows;
-    const int64_t nr = (rows - r0 < chunk_rows) ? rows - r0 : chunk_rows;
+    const int64_t r0 = bounds[c];
+    const int64_t nr = bounds[c + 1] - r0;
     const int64_t off = r0 * row_bytes, bytes = nr * row_bytes;
-    cudaEvent_t ev_in = pipe->event(1 + 2 * c), ev_k = pipe->event(2 + 2 * c);
-    if (ev_in == nullptr || ev_k == nullptr) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
-    QAT_TRY(cudaMemcpyAsync(dx + off, reinterpret_cast<const char*>(x_host) + off, bytes,
-                            cudaMemcpyHostToDevice, pipe->in));
-    if (bwd)
-      QAT_TRY(cudaMemcpyAsync(dg + off, reinterpret_cast<const char*>(g_host) + off, bytes,
-                              cudaMemcpyHostToDevice, pipe->in));
-    QAT_TRY(cudaEventRecord(ev_in, pipe->in));
-    QAT_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+    cudaEvent_t ev_in[2] = {pipe->event(1 + 3 * c), pipe->event(2 + 3 * c)}, ev_k = pipe->event(3 + 3 * c);
+    if (ev_in[0] == nullptr || ev_in[1] == nullptr || ev_k == nullptr)
+      return cuda_fail(cudaGetLastError(), "cudaEventCreate");
+    const char* src[2] = {reinterpret_cast<const char*>(x_host), reinterpret_cast<const char*>(g_host)};
+    char* dst_dev[2] = {dx, dg};
+    for (int l = 0; l < lanes; ++l) {
+      QAT_TRY(cudaMemcpyAsync(dst_dev[l] + off, src[l] + off, bytes, cudaMemcpyHostToDevice, pipe->in[l % kStreamsPerDirection]));
+      QAT_TRY(cudaEventRecord(ev_in[l], pipe->in[l % kStreamsPerDirection]));
+      QAT_TRY(cudaStreamWaitEvent(st, ev_in[l], 0));
+    }
     int rc = SYM ? qat_sym_fwd(dx + off, dy + off, nullptr, QAT_CODES_NONE, nullptr, nullptr, nullptr,
                                lo, hi, nr, cols, dtype, bits, nullptr, 0, st)
                  : qat_asym_fwd(dx + off, dy + off, nullptr, QAT_CODES_NONE, nullptr, nullptr, nullptr,
@@ -122,17 +168,19 @@ int fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_
       if (rc != QAT_OK) return rc;
     }
     QAT_TRY(cudaEventRecord(ev_k, st));
-    QAT_TRY(cudaStreamWaitEvent(pipe->out, ev_k, 0));
-    QAT_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(y_host) + off, dy + off, bytes,
-                            cudaMemcpyDeviceToHost, pipe->out));
-    if (bwd)
-      QAT_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(gx_host) + off, dgx + off, bytes,
-                              cudaMemcpyDeviceToHost, pipe->out));
+    const char* src_dev[2] = {dy, dgx};
+    char* dst[2] = {reinterpret_cast<char*>(y_host), reinterpret_cast<char*>(gx_host)};
+    for (int l = 0; l < lanes; ++l) {
+      QAT_TRY(cudaStreamWaitEvent(pipe->out[l % kStreamsPerDirection], ev_k, 0));
+      QAT_TRY(cudaMemcpyAsync(dst[l] + off, src_dev[l] + off, bytes, cudaMemcpyDeviceToHost, pipe->out[l % kStreamsPerDirection]));
+    }
   }
-  cudaEvent_t ev_done = pipe->event(1 + 2 * nchunks);
-  if (ev_done == nullptr) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
-  QAT_TRY(cudaEventRecord(ev_done, pipe->out));
-  QAT_TRY(cudaStreamWaitEvent(st, ev_done, 0));
+  for (int l = 0; l < lanes; ++l) {
+    cudaEvent_t ev_done = pipe->event(1 + 3 * nchunks + l);
+    if (ev_done == nullptr) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
+    QAT_TRY(cudaEventRecord(ev_done, pipe->out[l % kStreamsPerDirection]));
+    QAT_TRY(cudaStreamWaitEvent(st, ev_done, 0));
+  }
 #undef QAT_TRY
   return QAT_OK;
 }

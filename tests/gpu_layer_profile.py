@@ -33,9 +33,12 @@ for name, quant in (("b200_fused", llm_qat_b200.utils_quant), ("reference_eager"
         for _ in range(3): step()
         torch.cuda.synchronize()
     print(f"==== {name}: cpu-enqueue {t_cpu:.2f} ms/step, wall {t_all:.2f} ms/step")
-    evs = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == 'CUDA'] if hasattr(prof.key_averages()[0], 'device_type') else prof.key_averages()
-    rows = sorted(prof.key_averages(), key=lambda e: -getattr(e, 'self_device_time_total', 0))[:22]
-    tot = sum(getattr(e, 'self_device_time_total', 0) for e in prof.key_averages())
-    print(f"total device time per step: {tot/3/1e3:.2f} ms")
-    for e in rows:
-        print(f"{getattr(e,'self_device_time_total',0)/3/1e3:8.3f} ms  x{e.count//3:4d}  {e.key[:90]}")
+    ka = [e for e in prof.key_averages() if getattr(e, "device_type", None) is not None
+          and "CUDA" in str(e.device_type) and getattr(e, "self_device_time_total", 0) > 0]
+    tot = sum(e.self_device_time_total for e in ka)
+    ours = sum(e.self_device_time_total for e in ka if "qat::" in e.key)
+    gemm = sum(e.self_device_time_total for e in ka if "nvjet" in e.key or "gemm" in e.key.lower() or "cutlass" in e.key.lower())
+    print(f"device kernel time per step: {tot/3/1e3:.3f} ms = libqat_b200 {ours/3/1e3:.3f} + library GEMM {gemm/3/1e3:.3f} "
+          f"+ ATen (attention, norms, residuals, copies) {(tot-ours-gemm)/3/1e3:.3f}; {sum(e.count for e in ka)//3} launches")
+    for e in sorted(ka, key=lambda e: -e.self_device_time_total)[:45]:
+        print(f"{e.self_device_time_total/3/1e3:8.3f} ms  x{e.count//3:4d}  {e.key[:110]}")
