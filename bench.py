@@ -221,6 +221,53 @@ def time_config1_fp32(device, steps):
     return out
 
 
+def time_shape_sweep(device, steps, pk):
+    """SURVEY.md 8d config 1, the rest of it: both dtypes, the LLaMA-7B operand shapes, forward
+    alone and forward + backward, per quantizer.  Buffers rotate through > 2x L2 so that no
+    launch re-reads what a previous one left in the 126 MB L2."""
+    from llm_qat_b200 import _lib
+
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    g = torch.Generator().manual_seed(1234)
+    for dt_name, dt, tdt, esz in (("fp32", 0, torch.float32, 4), ("bf16", 1, torch.bfloat16, 2)):
+        for rows, cols in ((8192, 4096), (11008, 4096), (4096, 11008), (2048, 4096)):
+            n = rows * cols
+            nbuf = max(2, -(-300_000_000 // (n * esz * 2)))
+            xs = [(torch.randn(rows, cols, generator=g) * 0.5).to(tdt).to(device) for _ in range(min(nbuf, 2))]
+            while len(xs) < nbuf:
+                xs.append(xs[len(xs) % 2].clone())
+            gs = [torch.randn(rows, cols, generator=g).to(tdt).to(device)] * 1
+            gs = gs + [gs[0].clone() for _ in range(nbuf - 1)]
+            ys = [torch.empty_like(t) for t in xs]
+            ds = [torch.empty_like(t) for t in xs]
+            for qname, fn, bits in (("sym4", L.qat_sym_fwd, 4), ("sym8", L.qat_sym_fwd, 8), ("asym8", L.qat_asym_fwd, 8)):
+                res = {}
+                for mode in ("fwd", "fwd_bwd"):
+                    def once(i):
+                        _lib.check(fn(xs[i].data_ptr(), ys[i].data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, rows, cols, dt,
+                                      bits, 0, 0, st))
+                        if mode == "fwd_bwd":
+                            _lib.check(L.qat_ste_bwd(gs[i].data_ptr(), xs[i].data_ptr(), ds[i].data_ptr(), 0, -2.0,
+                                                     2.0, n, dt, st))
+                    for i in range(nbuf):
+                        once(i)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for k in range(steps):
+                        once(k % nbuf)
+                    e1.record()
+                    e1.synchronize()
+                    us = e0.elapsed_time(e1) / steps * 1e3
+                    nbytes = n * esz * (2 if mode == "fwd" else 5)
+                    res[mode] = {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                                 "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}
+                out[f"{dt_name}[{rows},{cols}] {qname}"] = res
+            del xs, gs, ys, ds
+    return out
+
+
 def time_qlinear(device, x, w, steps, pk):
     """K4: integer-grid tcgen05 GEMM at configs[1]; codes produced by K1."""
     from llm_qat_b200._lib import CODES_I8
@@ -413,6 +460,11 @@ def run_b200(args):
             extras["config1_fp32"] = time_config1_fp32(device, max(3, min(K, 20)))
         except Exception as e:
             extras["config1_fp32"] = {"error": f"{type(e).__name__}: {e}"}
+        if args.shape_sweep:
+            try:
+                extras["shape_sweep"] = time_shape_sweep(device, max(3, min(K, 20)), pk)
+            except Exception as e:
+                extras["shape_sweep"] = {"error": f"{type(e).__name__}: {e}"}
     # ---- BASELINE config 4: full LLaMA-7B W4A8KV4 QAT step with KD loss, data-parallel
     qat = None
     if not args.no_qat_step:
@@ -420,7 +472,12 @@ def run_b200(args):
             from harness import llama_qat as HQ
             from harness import qat_bench as QB
 
-            cfg7 = HQ.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4, num_hidden_layers=args.qat_layers)
+            if args.qat_model == "13b":   # BASELINE configs[4]: LLaMA-13B W4A8KV8 (180 GB/GPU sizing: DESIGN.md section 6)
+                cfg7 = HQ.QatConfig.llama_13b(w_bits=4, a_bits=8, kv_bits=8)
+                if args.qat_layers != 32:
+                    cfg7.num_hidden_layers = args.qat_layers
+            else:
+                cfg7 = HQ.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4, num_hidden_layers=args.qat_layers)
             del step, x, w, gx, gw
             torch.cuda.empty_cache()
             torch.cuda.reset_peak_memory_stats()
@@ -432,7 +489,8 @@ def run_b200(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
             qat = dict(r, ms_per_step=round(ms, 2), tokens_per_s=round(world * 2048 / ms * 1e3), n_gpus=world,
-                       model="LLaMA-7B dims, random init, student W4A8KV4 + frozen FP teacher, KD (KL batchmean), "
+                       model=("LLaMA-13B dims, random init, student W4A8KV8" if args.qat_model == "13b" else
+                              "LLaMA-7B dims, random init, student W4A8KV4") + " + frozen FP teacher, KD (KL batchmean), "
                              "grad checkpointing, AdamW, bf16" + (", DDP/NCCL all-reduce" if world > 1 else ""))
         except Exception as e:  # keep the headline line even if the big model cannot run
             qat = {"error": f"{type(e).__name__}: {e}"}
@@ -533,6 +591,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qat-step", action="store_true", help="skip the LLaMA-7B QAT-step extra (config 4)")
     ap.add_argument("--qat-layers", type=int, default=32)
+    ap.add_argument("--shape-sweep", action="store_true",
+                    help="add per-shape / per-dtype / per-quantizer kernel timings (SURVEY.md 8d config 1)")
+    ap.add_argument("--qat-model", default="7b", choices=["7b", "13b"],
+                    help="model of the QAT-step extra: 7b = BASELINE configs[3], 13b = configs[4] (W4A8KV8)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -150,6 +150,18 @@ __device__ __forceinline__ float load_scalar(const void* x, int64_t i) {
   return bf16lo(reinterpret_cast<const uint16_t*>(x)[i]);
 }
 
+// AsymScale's packed-bf16 chain, callable from code that is also instantiated for SymScale
+template <int DT>
+__device__ __forceinline__ bool sc_packed(const AsymScale<DT>& sc) { return sc.packed; }
+template <int DT>
+__device__ __forceinline__ bool sc_packed(const SymScale<DT>&) { return false; }
+template <int DT>
+__device__ __forceinline__ uint32_t sc_pair(const AsymScale<DT>& sc, uint32_t w, float* c0, float* c1) {
+  return sc.pair_bf16(w, c0, c1);
+}
+template <int DT>
+__device__ __forceinline__ uint32_t sc_pair(const SymScale<DT>&, uint32_t w, float*, float*) { return w; }
+
 // ---- per-vector quantize + all outputs ------------------------------------
 // `e0` = flat element index of the vector's first element.
 template <int DT, bool SYM, bool FAST, typename Scale>
@@ -164,6 +176,14 @@ __device__ __forceinline__ void emit_vec(const FwdParams& p, const Scale& sc, co
       const uint32_t pw = mul_bf16x2(w[j], sc.s2);  // fl_bf16(x * s), two elements
       yv[(2 * j) % N] = sc.template apply_p<FAST>(bf16lo(pw), &qv[(2 * j) % N]);
       yv[(2 * j + 1) % N] = sc.template apply_p<FAST>(bf16hi(pw), &qv[(2 * j + 1) % N]);
+    }
+  } else if (!SYM && DT == QAT_BF16 && FAST && sc_packed(sc)) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t yw = sc_pair(sc, w[j], &qv[(2 * j) % N], &qv[(2 * j + 1) % N]);
+      yv[(2 * j) % N] = bf16lo(yw);
+      yv[(2 * j + 1) % N] = bf16hi(yw);
     }
   } else {
 #pragma unroll
@@ -308,7 +328,8 @@ __device__ __forceinline__ typename ScaleOf<DT, SYM>::type warp_derive_scale(con
     sc.ra.r1 = __shfl_sync(kFull, sc.ra.r1, 0);
     sc.S = qmax;
     sc.rS = __shfl_sync(kFull, sc.rS, 0);
-    sc.fast = recip_range_ok(sc.a) && (sc.beta == sc.beta);
+    sc.ra_rn = __shfl_sync(kFull, sc.ra_rn, 0);
+    sc.finish();
   }
   return sc;
 }
@@ -334,6 +355,10 @@ __device__ __forceinline__ uint4 quant_vec_y(const Scale& sc, const uint4& v) {
       }
     }
     o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  } else if (!SYM && DT == QAT_BF16 && FAST && sc_packed(sc)) {
+    float c0, c1;
+    o = make_uint4(sc_pair(sc, v.x, &c0, &c1), sc_pair(sc, v.y, &c0, &c1), sc_pair(sc, v.z, &c0, &c1),
+                   sc_pair(sc, v.w, &c0, &c1));
   } else {
     constexpr int N = Num<DT>::kPerVec;
     float yv[N], q;
@@ -369,6 +394,10 @@ __device__ __forceinline__ void quant_vec_feed(const FwdParams& p, const Scale& 
   } else if constexpr (SYM) {
 #pragma unroll
     for (int i = 0; i < N; ++i) qv[i] = rintf(Num<DT>::fl(__fmul_rn(vec_get<DT>(v, i), sc.s)));
+  } else if (DT == QAT_BF16 && FAST && sc_packed(sc)) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) (void)sc_pair(sc, w[k], &qv[(2 * k) % N], &qv[(2 * k + 1) % N]);
   } else {
 #pragma unroll
     for (int i = 0; i < N; ++i) (void)sc.template apply<FAST>(vec_get<DT>(v, i), &qv[i]);

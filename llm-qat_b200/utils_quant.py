@@ -56,6 +56,25 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device):
+    """Device guard for a launch: free when ``device`` is already current (the
+    usual case — torch.cuda.device() costs ~10 us of host time per use)."""
+    if device.index is None or torch.cuda.current_device() == device.index:
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -120,7 +139,7 @@ def fake_quant_forward(input: torch.Tensor, num_bits: int, layerwise: bool, symm
     ws_bytes = L.qat_fwd_workspace_bytes(rows, cols, dt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     fn = L.qat_sym_fwd if symmetric else L.qat_asym_fwd
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = fn(x.data_ptr(), _ptr(y), _ptr(codes), codes_kind, _ptr(st0), _ptr(st1), _ptr(mask),
                 lo, hi, rows, cols, dt, int(num_bits), _ptr(ws), ws_bytes, _stream_ptr(dev))
     check(rc, "qat_sym_fwd" if symmetric else "qat_asym_fwd")
@@ -145,7 +164,7 @@ def ste_backward(grad_output: torch.Tensor, input: torch.Tensor, clip_val, *, wa
     if n == 0:
         return (gx, None) if want_mask else gx
     mask = torch.empty((n + 7) // 8, dtype=torch.uint8, device=g.device) if want_mask else None
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         rc = _lib.lib().qat_ste_bwd(g.data_ptr(), x.data_ptr(), gx.data_ptr(), _ptr(mask), lo, hi, n, dt,
                                     _stream_ptr(g.device))
     check(rc, "qat_ste_bwd")
@@ -160,7 +179,7 @@ def ste_backward_from_mask(grad_output: torch.Tensor, mask: torch.Tensor):
     gx = torch.empty_like(g)
     if g.numel() == 0:
         return gx
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         rc = _lib.lib().qat_ste_bwd_from_mask(g.data_ptr(), mask.data_ptr(), gx.data_ptr(), g.numel(), dt,
                                               _stream_ptr(g.device))
     check(rc, "qat_ste_bwd_from_mask")
@@ -213,7 +232,7 @@ class _LowBitWeight(torch.autograd.Function):
         L = _lib.lib()
         ws_bytes = int(L.qat_lowbit_workspace_bytes(rows, int(bool(layerwise))))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
-        with torch.cuda.device(w.device):
+        with _on(w.device):
             rc = L.qat_lowbit_weight_fwd(w.data_ptr(), out.data_ptr(), rows, cols, dt, int(w_bits),
                                          int(bool(layerwise)), _ptr(ws), ws_bytes, _stream_ptr(w.device))
         check(rc, "qat_lowbit_weight_fwd")
@@ -305,7 +324,7 @@ class _QuantLinearFn(torch.autograd.Function):
         xe, xm, _ = _feed_layout(T, K)
         we, wm, _ = _feed_layout(N, K)
         xb, wb = xblob.data_ptr(), wblob.data_ptr()
-        with torch.cuda.device(dev):
+        with _on(dev):
             rc = _lib.lib().qat_qlinear_fused_fwd(
                 x2.data_ptr(), w.data_ptr(), out.data_ptr(), xb, xb + xe, xb + xm, wb, wb + we, wb + wm,
                 T, N, K, dt, int(a_bits), int(w_bits), -2.0, 2.0,  # clip: utils_quant.py:198,245
@@ -326,19 +345,34 @@ class _QuantLinearFn(torch.autograd.Function):
         xblob, wblob = ctx.saved_tensors
         T, N, K = ctx.dims
         g2 = grad_output.reshape(T, N)
-        g2 = g2 if g2.is_contiguous() else g2.contiguous()
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        dev, dtype = g2.device, ctx.dtype
+        dt = _DTYPES[dtype]
+        L = _lib.lib()
+        xb, wb = xblob.data_ptr(), wblob.data_ptr()
+        xe, xm, _ = _feed_layout(T, K)
+        we, wm, _ = _feed_layout(N, K)
         gx = gw = None
-        if ctx.needs_input_grad[0]:
-            qw, ew, _ = _feed_views(wblob, N, K)
-            _, _, mx = _feed_views(xblob, T, K)
-            wq = dequant_codes(qw, ew, ctx.dtype)                        # == reference's fake-quant W
-            gx = ste_backward_from_mask(g2 @ wq, mx).view(ctx.in_shape)
-            del wq
-        if ctx.needs_input_grad[1]:
-            qx, ex, _ = _feed_views(xblob, T, K)
-            _, _, mw = _feed_views(wblob, N, K)
-            xq = dequant_codes(qx, ex, ctx.dtype)                        # == reference's fake-quant x
-            gw = ste_backward_from_mask(g2.t() @ xq, mw)
+        with _on(dev):
+            stream = _stream_ptr(dev)
+            if ctx.needs_input_grad[0]:
+                wq = torch.empty((N, K), dtype=dtype, device=dev)           # == the reference's fake-quant W
+                check(L.qat_dequant_codes(wb, wb + we, wq.data_ptr(), N, K, dt, stream), "qat_dequant_codes")
+                t = torch.mm(g2, wq)
+                del wq
+                gx = torch.empty_like(t)
+                check(L.qat_ste_bwd_from_mask(t.data_ptr(), xb + xm, gx.data_ptr(), T * K, dt, stream),
+                      "qat_ste_bwd_from_mask")
+                gx = gx.view(ctx.in_shape)
+            if ctx.needs_input_grad[1]:
+                xq = torch.empty((T, K), dtype=dtype, device=dev)           # == the reference's fake-quant x
+                check(L.qat_dequant_codes(xb, xb + xe, xq.data_ptr(), T, K, dt, stream), "qat_dequant_codes")
+                t = torch.mm(g2.t(), xq)
+                del xq
+                gw = torch.empty_like(t)
+                check(L.qat_ste_bwd_from_mask(t.data_ptr(), wb + wm, gw.data_ptr(), N * K, dt, stream),
+                      "qat_ste_bwd_from_mask")
         return gx, gw, None, None, None
 
 
@@ -346,7 +380,7 @@ def dequant_codes(codes, row_e, dtype):
     """out[r, c] = codes[r, c] / row_e[r] in ``dtype`` (exact IEEE quotient, one rounding)."""
     rows, cols = codes.shape
     out = torch.empty((rows, cols), dtype=dtype, device=codes.device)
-    with torch.cuda.device(codes.device):
+    with _on(codes.device):
         rc = _lib.lib().qat_dequant_codes(codes.data_ptr(), row_e.data_ptr(), out.data_ptr(), rows, cols,
                                           _DTYPES[dtype], _stream_ptr(codes.device))
     check(rc, "qat_dequant_codes")
@@ -358,7 +392,7 @@ def qlinear_i8(qx, qw, ex, ew, out_dtype):
     T, K = qx.shape
     N = qw.shape[0]
     out = torch.empty((T, N), dtype=out_dtype, device=qx.device)
-    with torch.cuda.device(qx.device):
+    with _on(qx.device):
         rc = _lib.lib().qat_qlinear_i8_fwd(qx.data_ptr(), qw.data_ptr(), ex.data_ptr(), ew.data_ptr(),
                                            out.data_ptr(), T, N, K, _DTYPES[out_dtype], _stream_ptr(qx.device))
     check(rc, "qat_qlinear_i8_fwd")

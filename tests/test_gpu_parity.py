@@ -178,6 +178,46 @@ def test_unaligned_and_noncontiguous_inputs():
         SymQuantizer.apply(torch.zeros(2, 3, 4, 8).cuda().transpose(1, 2), CLIP, 4, False)
 
 
+# --------------------------------------------------------------- config 5: LLaMA-13B shapes, 8 shards
+@pytest.mark.parametrize("shape,bits,what", [
+    ((13824, 5120), 4, "gate/up_proj weight: sharded by output channel"),
+    ((5120, 13824), 4, "down_proj weight: sharded by output channel"),
+    ((1, 2048, 5120), 8, "K/V of one sequence, KV8: sharded by token"),
+])
+def test_config5_shards_reassemble_bit_exact(shape, bits, what):
+    """BASELINE configs[4]: every statistic is row-local, so the 8 row shards a box of 8 GPUs
+    would process (sharding.row_partition) must reproduce the unsharded tensor bit for bit —
+    dequantized values, int8 codes, row divisors and STE masks alike (no data-path collective)."""
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.sharding import row_partition
+    from llm_qat_b200.utils_quant import fake_quant_forward, ste_backward
+
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(*shape, generator=gen) * (0.02 if len(shape) == 2 else 1.0)).bfloat16().cuda()
+    g = torch.randn(*shape, generator=gen).bfloat16().cuda()
+    flat, gflat = x.reshape(-1, shape[-1]), g.reshape(-1, shape[-1])
+    y, _, _, _, _ = fake_quant_forward(flat, bits, False, True)
+    _, codes, _, e, mask = fake_quant_forward(flat, bits, False, True, want_y=False, codes_kind=CODES_I8,
+                                              want_scales=True, mask_clip=(-2.0, 2.0))
+    gx = ste_backward(gflat, flat, CLIP)
+    world, rows = 8, flat.shape[0]
+    ys, cs, es, ms, gs = [], [], [], [], []
+    for rank in range(world):
+        r0, n = row_partition(rows, world, rank)
+        part = flat[r0:r0 + n]
+        ys.append(fake_quant_forward(part, bits, False, True)[0])
+        _, c, _, ee, m = fake_quant_forward(part, bits, False, True, want_y=False, codes_kind=CODES_I8,
+                                            want_scales=True, mask_clip=(-2.0, 2.0))
+        cs.append(c); es.append(ee); ms.append(m)
+        gs.append(ste_backward(gflat[r0:r0 + n], part, CLIP))
+    assert torch.equal(torch.cat(ys).view(torch.int16), y.view(torch.int16)), what
+    assert torch.equal(torch.cat(cs), codes) and torch.equal(torch.cat(es), e), what
+    assert torch.equal(torch.cat(ms), mask), what          # shard sizes are multiples of 8 elements
+    assert torch.equal(torch.cat(gs).view(torch.int16), gx.view(torch.int16)), what
+    # and the unsharded result is the oracle's
+    assert qo.count_mismatch(U.tensor_to_f32(y[:64]), qo.sym_forward(U.tensor_to_f32(flat[:64]), bits, False, "bf16")["y"]) == 0
+
+
 # --------------------------------------------------------------- full BASELINE sizes: properties
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_config1_full_size_properties(dtype):

@@ -1,5 +1,7 @@
 """CPU: the oracle restatement vs the golden vectors generated from the live
 reference (oracle/gen_golden.py), plus structural properties of the arithmetic."""
+import os
+
 import numpy as np
 import pytest
 
@@ -117,3 +119,22 @@ def test_bf16_round_is_nearest_even():
     np.testing.assert_array_equal(r[:4], np.array([1.0, 1.0, 1.015625, 1.0078125], dtype=np.float32))
     assert np.isinf(r[4]) and np.signbit(r[5])
     assert np.isnan(qo.bf16_round(np.array([np.nan], dtype=np.float32)))[0]
+
+
+def test_bf16_reciprocal_quotient_proof(tmp_path):
+    """The packed-bf16 AsymQuantizer chain of K2 replaces the reference's two divisions by
+    multiplications with per-row reciprocals and its add/sub by single-rounding bf16x2
+    instructions.  oracle/proofs/bf16_quotient_by_reciprocal.c checks both claims exhaustively
+    (4.2e8 quotients; 4.26e9 add/sub pairs): compile and run it."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "proofs",
+                       "bf16_quotient_by_reciprocal.c")
+    exe = str(tmp_path / "bf16q")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", src, "-o", exe], check=True)
+    for args in ([], ["addsub"]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout + r.stderr
