@@ -123,6 +123,12 @@ int qat_lowbit_weight_fwd(const void* w, void* w_eff, int64_t rows, int64_t cols
 int qat_qlinear_i8_fwd(const int8_t* qx, const int8_t* qw, const float* ex, const float* ew,
                        void* out, int64_t T, int64_t N, int64_t K, int out_dtype, void* stream);
 
+/* Programmatic dependent launch for the hot kernels (K1-K4, dequant): 1 (default) lets a
+ * kernel's CTAs be scheduled while the previous kernel of the stream drains — no memory is
+ * touched before that grid has completed (griddepcontrol.wait); 0 = plain stream order.
+ * Also settable once through the environment, QAT_B200_PDL=0. */
+int qat_set_pdl(int enabled);
+
 /* Tuning knob of the contraction: CTAs per tcgen05.mma.  2 = CTA pairs on 256x256
  * tiles (cta_group::2), 1 = single CTAs on 128x256 tiles, 0 = choose per problem
  * (the default; also settable once through the environment, QAT_B200_GEMM_CG). */

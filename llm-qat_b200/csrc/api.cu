@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -23,6 +24,20 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
   return (int)e;
 }
+
+namespace {
+std::atomic<int> g_pdl{-1};  // -1: read QAT_B200_PDL on first use
+}
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("QAT_B200_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -49,6 +64,11 @@ int qat_version(void) { return QAT_B200_VERSION; }
 const char* qat_last_error(void) { return qat::g_err; }
 
 uint64_t qat_launch_count(void) { return qat::g_launches.load(std::memory_order_relaxed); }
+
+int qat_set_pdl(int enabled) {
+  qat::set_pdl(enabled);
+  return QAT_OK;
+}
 
 int qat_check_device(void) {
   int n = 0;

@@ -445,6 +445,8 @@ __global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
   // keep the 64-bit row base in registers: without this the compiler re-derives
   // row * nvec under every load's predicate (5 extra instructions per vector)
   asm volatile("" : "+l"(xrow));
+  pdl_wait();               // the previous grid's results are visible from here on
+  pdl_launch_dependents();  // the next kernel's CTAs may queue up behind this grid's
 
   uint4 v[ITERS];
 #pragma unroll
@@ -734,11 +736,11 @@ Plan make_plan(const void* x, const void* y, int64_t rows, int64_t cols, int dty
 template <int DT, bool SYM, int ITERS>
 void launch_vec_iters(const FwdParams& p, const Plan& pl, unsigned grid, int out, cudaStream_t st) {
   if (out == OUT_Y)
-    rowquant_vec_kernel<DT, ITERS, SYM, OUT_Y><<<grid, pl.block, 0, st>>>(p);
+    (void)launch_pdl(rowquant_vec_kernel<DT, ITERS, SYM, OUT_Y>, dim3(grid), dim3(pl.block), 0, st, p);
   else if (out == OUT_FEED)
-    rowquant_vec_kernel<DT, ITERS, SYM, OUT_FEED><<<grid, pl.block, 0, st>>>(p);
+    (void)launch_pdl(rowquant_vec_kernel<DT, ITERS, SYM, OUT_FEED>, dim3(grid), dim3(pl.block), 0, st, p);
   else
-    rowquant_vec_kernel<DT, ITERS, SYM, OUT_ANY><<<grid, pl.block, 0, st>>>(p);
+    (void)launch_pdl(rowquant_vec_kernel<DT, ITERS, SYM, OUT_ANY>, dim3(grid), dim3(pl.block), 0, st, p);
 }
 
 template <int DT, bool SYM, bool VEC>

@@ -322,6 +322,10 @@ qlinear_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // peers touch our barriers: cluster-wide
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + C::tmem_ptr);
+  // barrier init, TMEM allocation and descriptor prefetch above overlap the previous
+  // kernel's tail; its results (the codes K1 wrote) are read only from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own rows) =====================
@@ -502,13 +506,15 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, qlinear_i8_kernel<OUT_DT, CG>, ma, mb, p);
   if (e != cudaSuccess) return cuda_fail(e, "qlinear_i8_kernel launch");
   QAT_CHECK_LAUNCH("qlinear_i8_kernel");

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const BwdParams p) {
   const char* g = reinterpret_cast<const char*>(p.g);
   const char* x = reinterpret_cast<const char*>(p.x);
   char* gx = reinterpret_cast<char*>(p.gx);
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t base = (int64_t)blockIdx.x * kTile; base < p.nvec; base += (int64_t)gridDim.x * kTile) {
     uint4 gv[kUnroll], xv[kUnroll];
     uint32_t mb[kUnroll];
@@ -201,9 +203,9 @@ int bwd_entry(const void* g, const void* x, const uint8_t* mask_in, void* gx, ui
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     if (dtype == QAT_F32)
-      ste_bwd_kernel<QAT_F32, FROM_MASK><<<(unsigned)grid, kThreads, 0, st>>>(p);
+      (void)launch_pdl(ste_bwd_kernel<QAT_F32, FROM_MASK>, dim3((unsigned)grid), dim3(kThreads), 0, st, p);
     else
-      ste_bwd_kernel<QAT_BF16, FROM_MASK><<<(unsigned)grid, kThreads, 0, st>>>(p);
+      (void)launch_pdl(ste_bwd_kernel<QAT_BF16, FROM_MASK>, dim3((unsigned)grid), dim3(kThreads), 0, st, p);
     QAT_CHECK_LAUNCH("ste_bwd_kernel");
   } else {
     if (mask_out != nullptr) {
