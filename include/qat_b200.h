@@ -98,6 +98,12 @@ int qat_asym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row
 int qat_ste_bwd(const void* g, const void* x, void* gx, uint8_t* mask_out, float clip_lo,
                 float clip_hi, int64_t n, int dtype, void* stream);
 
+/* Same backward with the clip bounds {lo, hi} read in-kernel from DEVICE memory (two floats):
+ * a CUDA clip_val costs no host synchronisation (the reference indexes clip_val[0] / [1] as
+ * 0-dim tensors, utils_quant.py:85-86).  Bounds are rounded to x's dtype, like x.ge(clip_val[1]). */
+int qat_ste_bwd_devclip(const void* g, const void* x, void* gx, uint8_t* mask_out, const float* clip_dev,
+                        int64_t n, int dtype, void* stream);
+
 /* Same backward, driven by a forward-emitted packed mask instead of x
  * (reads 2e + 1/8 bytes per element instead of 3e). */
 int qat_ste_bwd_from_mask(const void* g, const uint8_t* mask, void* gx, int64_t n, int dtype,

@@ -33,6 +33,8 @@ def _declare(lib):
         "qat_asym_fwd": (I, [P, P, P, I, P, P, P, F, F, L, L, I, I, P, Z, P]),
         # g, x, gx, mask_out, lo, hi, n, dtype, stream
         "qat_ste_bwd": (I, [P, P, P, P, F, F, L, I, P]),
+        # g, x, gx, mask_out, clip_dev, n, dtype, stream
+        "qat_ste_bwd_devclip": (I, [P, P, P, P, P, L, I, P]),
         # g, mask, gx, n, dtype, stream
         "qat_ste_bwd_from_mask": (I, [P, P, P, L, I, P]),
         "qat_lowbit_workspace_bytes": (Z, [L, I]),

@@ -21,6 +21,7 @@ struct BwdParams {
   void* gx;
   uint8_t* mask_out;  // optional
   float lo, hi;       // rounded to the tensor dtype on the host
+  const float* clip_dev;  // optional: {lo, hi} in device memory (a CUDA clip_val), read in-kernel
   int64_t n;          // elements
   int64_t nvec;       // full 16-byte vectors
 };
@@ -66,6 +67,11 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const BwdParams p) {
   char* gx = reinterpret_cast<char*>(p.gx);
   pdl_wait();
   pdl_launch_dependents();
+  float lo = p.lo, hi = p.hi;
+  if (!FROM_MASK && p.clip_dev != nullptr) {  // compared in x's dtype, like x.ge(clip_val[1])
+    lo = Num<DT>::fl(p.clip_dev[0]);
+    hi = Num<DT>::fl(p.clip_dev[1]);
+  }
   for (int64_t base = (int64_t)blockIdx.x * kTile; base < p.nvec; base += (int64_t)gridDim.x * kTile) {
     uint4 gv[kUnroll], xv[kUnroll];
     uint32_t mb[kUnroll];
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const BwdParams p) {
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = base + (int64_t)u * kThreads + threadIdx.x;
       const bool valid = j < p.nvec;
-      const uint32_t pass = FROM_MASK ? mb[u] : pass_bits<DT>(xv[u], p.lo, p.hi);
+      const uint32_t pass = FROM_MASK ? mb[u] : pass_bits<DT>(xv[u], lo, hi);
       if (valid) stg_stream(gx + j * 16, apply_pass<DT>(gv[u], pass));
       if (!FROM_MASK && p.mask_out != nullptr) {
         if (N == 8) {
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const BwdParams p) {
       } else {
         const float xf = (DT == QAT_F32) ? reinterpret_cast<const float*>(p.x)[i]
                                          : bf16lo(reinterpret_cast<const uint16_t*>(p.x)[i]);
-        pass = !(xf >= p.hi || xf <= p.lo);
+        pass = !(xf >= hi || xf <= lo);
       }
       if (DT == QAT_F32) {
         const uint32_t gvb = reinterpret_cast<const uint32_t*>(p.g)[i];
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const BwdParams p) {
           if (i2 >= p.n) break;
           const float xf = (DT == QAT_F32) ? reinterpret_cast<const float*>(p.x)[i2]
                                            : bf16lo(reinterpret_cast<const uint16_t*>(p.x)[i2]);
-          bits |= ((xf >= p.hi || xf <= p.lo) ? 0u : 1u) << k;
+          bits |= ((xf >= hi || xf <= lo) ? 0u : 1u) << k;
         }
         p.mask_out[b] = (uint8_t)bits;
       }
@@ -151,6 +157,11 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_kernel(const BwdParams p) {
 // unaligned pointers: one element per thread
 template <int DT, bool FROM_MASK>
 __global__ void __launch_bounds__(kThreads) ste_bwd_scalar_kernel(const BwdParams p) {
+  float lo = p.lo, hi = p.hi;
+  if (!FROM_MASK && p.clip_dev != nullptr) {
+    lo = Num<DT>::fl(p.clip_dev[0]);
+    hi = Num<DT>::fl(p.clip_dev[1]);
+  }
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n;
        i += (int64_t)gridDim.x * kThreads) {
     bool pass;
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) ste_bwd_scalar_kernel(const BwdParam
     } else {
       const float xf = (DT == QAT_F32) ? reinterpret_cast<const float*>(p.x)[i]
                                        : bf16lo(reinterpret_cast<const uint16_t*>(p.x)[i]);
-      pass = !(xf >= p.hi || xf <= p.lo);
+      pass = !(xf >= hi || xf <= lo);
     }
     if (DT == QAT_F32) {
       const uint32_t gvb = reinterpret_cast<const uint32_t*>(p.g)[i];
@@ -175,7 +186,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <bool FROM_MASK>
 int bwd_entry(const void* g, const void* x, const uint8_t* mask_in, void* gx, uint8_t* mask_out,
-              float lo, float hi, int64_t n, int dtype, void* stream) {
+              float lo, float hi, int64_t n, int dtype, void* stream, const float* clip_dev = nullptr) {
   QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16, "dtype must be QAT_F32 or QAT_BF16 (got %d)", dtype);
   QAT_CHECK_ARG(n >= 0, "negative element count");
   if (n == 0) return QAT_OK;
@@ -190,6 +201,7 @@ int bwd_entry(const void* g, const void* x, const uint8_t* mask_in, void* gx, ui
   p.mask_out = mask_out;
   p.lo = dtype == QAT_F32 ? lo : __bfloat162float(__float2bfloat16_rn(lo));
   p.hi = dtype == QAT_F32 ? hi : __bfloat162float(__float2bfloat16_rn(hi));
+  p.clip_dev = clip_dev;
   p.n = n;
   const int per = dtype == QAT_F32 ? 4 : 8;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -232,6 +244,15 @@ extern "C" {
 int qat_ste_bwd(const void* g, const void* x, void* gx, uint8_t* mask_out, float clip_lo,
                 float clip_hi, int64_t n, int dtype, void* stream) {
   return qat::bwd_entry<false>(g, x, nullptr, gx, mask_out, clip_lo, clip_hi, n, dtype, stream);
+}
+
+int qat_ste_bwd_devclip(const void* g, const void* x, void* gx, uint8_t* mask_out, const float* clip_dev,
+                        int64_t n, int dtype, void* stream) {
+  if (clip_dev == nullptr) {
+    qat::set_error("clip_dev is NULL");
+    return QAT_ERR_BAD_ARG;
+  }
+  return qat::bwd_entry<false>(g, x, nullptr, gx, mask_out, 0.f, 0.f, n, dtype, stream, clip_dev);
 }
 
 int qat_ste_bwd_from_mask(const void* g, const uint8_t* mask, void* gx, int64_t n, int dtype,

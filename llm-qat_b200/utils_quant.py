@@ -155,7 +155,6 @@ def ste_backward(grad_output: torch.Tensor, input: torch.Tensor, clip_val, *, wa
     if grad_output.shape != input.shape:
         raise RuntimeError(f"STE backward: grad shape {tuple(grad_output.shape)} != input shape {tuple(input.shape)}")
     dt = _dtype_code(input)
-    lo, hi = _clip_bounds(clip_val)
     g = grad_output if grad_output.is_contiguous() else grad_output.contiguous()
     x = input.detach()
     x = x if x.is_contiguous() else x.contiguous()
@@ -164,6 +163,15 @@ def ste_backward(grad_output: torch.Tensor, input: torch.Tensor, clip_val, *, wa
     if n == 0:
         return (gx, None) if want_mask else gx
     mask = torch.empty((n + 7) // 8, dtype=torch.uint8, device=g.device) if want_mask else None
+    if isinstance(clip_val, torch.Tensor) and clip_val.is_cuda:
+        # a CUDA clip_val is read by the kernel: no .item()/.tolist() synchronisation
+        clip_dev = clip_val.detach().reshape(-1)[:2].to(device=g.device, dtype=torch.float32).contiguous()
+        with _on(g.device):
+            rc = _lib.lib().qat_ste_bwd_devclip(g.data_ptr(), x.data_ptr(), gx.data_ptr(), _ptr(mask),
+                                                clip_dev.data_ptr(), n, dt, _stream_ptr(g.device))
+        check(rc, "qat_ste_bwd_devclip")
+        return (gx, mask) if want_mask else gx
+    lo, hi = _clip_bounds(clip_val)
     with _on(g.device):
         rc = _lib.lib().qat_ste_bwd(g.data_ptr(), x.data_ptr(), gx.data_ptr(), _ptr(mask), lo, hi, n, dt,
                                     _stream_ptr(g.device))

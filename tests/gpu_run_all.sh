@@ -18,4 +18,8 @@ if [ "$1" == "ncu" ]; then
   $CMD > gpurun_out/plain2.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'rowquant_vec_kernel|ste_bwd_kernel|qlinear_i8_kernel' -s 16 -c 9 -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
+  # K4 alone at config 2 (CTA-pair plan), same call: one more capture
+  python tests/gpu_gemm_only.py 5 2 > gpurun_out/gemm_plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:qlinear_i8_kernel -s 4 -c 1 -f -o gpurun_out/prof_gemm python tests/gpu_gemm_only.py 5 2 > gpurun_out/ncu_gemm.log 2>&1
+  echo "ncu gemm rc=$?"
 fi

@@ -81,8 +81,9 @@ def main():
         summary["step_share_from_launch_list"] = {k: {"mean_us": round(v, 2), "share": round(v / tot, 4)}
                                                   for k, v in step.items()}
     # ---- full capture ------------------------------------------------------
-    rep = os.path.join(OUT, "prof.ncu-rep")
-    if os.path.exists(rep):
+    for rep in (os.path.join(OUT, "prof.ncu-rep"), os.path.join(OUT, "prof_gemm.ncu-rep")):
+        if not os.path.exists(rep):
+            continue
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
@@ -99,6 +100,7 @@ def main():
                         ent[w] = to_bytes(r[idx[w]], units[idx[w]])
             ent["dram_bytes_per_launch"] = ent.get("dram__bytes_read.sum", 0) + ent.get("dram__bytes_write.sum", 0)
             summary["full_capture"].append(ent)
+    if summary["full_capture"]:
         # map onto bench.py's kernel names by order of appearance: x, W, bwd x, bwd W
         by = collections.defaultdict(list)
         for e in summary["full_capture"]:

@@ -136,6 +136,29 @@ def test_backward_mask_variants_agree(dtype):
             assert torch.equal(fmask, mask)
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_cuda_clip_val_is_read_in_kernel(dtype):
+    """clip_val may live on the GPU (the reference indexes it as 0-dim tensors, :85-86): the kernel
+    reads the two bounds itself — same result as the host-scalar path, for bounds that are and are
+    not representable in the tensor dtype (x.ge(clip) compares in x's dtype)."""
+    from llm_qat_b200 import AsymQuantizer, SymQuantizer
+
+    gen = torch.Generator().manual_seed(9)
+    x = (torch.randn(33, 1000, generator=gen) * 1.5).to(U.DTYPES[dtype])
+    x.view(-1)[:6] = torch.tensor([2.0, -2.0, 1.703125, -1.296875, 1.7, -1.3]).to(x.dtype)
+    g = torch.randn(33, 1000, generator=gen).to(U.DTYPES[dtype])
+    for clip in ([-2.0, 2.0], [-1.3, 1.7]):
+        outs = []
+        for dev in ("cpu", "cuda"):
+            for Q in (SymQuantizer, AsymQuantizer):
+                xi = x.cuda().requires_grad_(True)
+                Q.apply(xi, torch.tensor(clip, device=dev), 8, False).backward(g.cuda())
+                outs.append(xi.grad)
+        want = qo.ste_backward(U.tensor_to_f32(g), U.tensor_to_f32(x), clip[0], clip[1], dtype)["gx"]
+        for o in outs:
+            assert qo.count_mismatch(U.tensor_to_f32(o), want) == 0, (clip, dtype)
+
+
 # --------------------------------------------------------------- shapes / modes at scale vs oracle
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape,lw", [
