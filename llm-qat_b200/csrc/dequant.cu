@@ -18,12 +18,15 @@ template <int DT>
 __device__ __forceinline__ void dequant_vec(const uint4& c, float e, void* out, int64_t j) {
   const bool fast = recip_range_ok(e);
   const float r = __frcp_rn(e);
+  // bf16 output and a bf16-valued divisor (what K1 emits for bf16 tensors): one multiply is
+  // exact — see SymScale::mulq in common.cuh
+  const bool mulq = DT == QAT_BF16 && fast && Num<QAT_BF16>::fl(e) == e;
   const uint32_t w[4] = {c.x, c.y, c.z, c.w};
   float y[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const float q = (float)(int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-    y[k] = fast ? div_code_by_recip(q, e, r) : __fdiv_rn(q, e);
+    y[k] = mulq ? __fmul_rn(q, r) : fast ? div_code_by_recip(q, e, r) : __fdiv_rn(q, e);
   }
   if (DT == QAT_BF16) {
     uint4* o = reinterpret_cast<uint4*>(out) + 2 * j;

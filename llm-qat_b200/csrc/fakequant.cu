@@ -320,8 +320,7 @@ __device__ __forceinline__ typename ScaleOf<DT, SYM>::type warp_derive_scale(con
     sc.s = __shfl_sync(kFull, sc.s, 0);
     sc.e = __shfl_sync(kFull, sc.e, 0);
     sc.r = __shfl_sync(kFull, sc.r, 0);
-    sc.s2 = pack_bf16x2(sc.s, sc.s);
-    sc.fast = recip_range_ok(sc.e);
+    sc.finish(qmax);
   } else {
     sc.a = __shfl_sync(kFull, sc.a, 0);
     sc.beta = __shfl_sync(kFull, sc.beta, 0);
@@ -345,7 +344,9 @@ __device__ __forceinline__ uint4 quant_vec_y(const Scale& sc, const uint4& v) {
     for (int j = 0; j < 4; ++j) {
       const uint32_t pw = mul_bf16x2(w[j], sc.s2);  // fl_bf16(x * s), two elements
       const float c0 = rintf(bf16lo(pw)), c1 = rintf(bf16hi(pw));
-      if (FAST) {
+      if (FAST && sc.mulq) {
+        ow[j] = pack_bf16x2(__fmul_rn(c0, sc.r), __fmul_rn(c1, sc.r));   // == fl_bf16(c / e), see SymScale
+      } else if (FAST) {
         // sign(y) == sign(p) always (e > 0); restoring it on the packed pair also
         // turns the +0 that the remainder step gives for c = -0 back into -0.
         ow[j] = pack_bf16x2(div_code_by_recip(c0, sc.e, sc.r), div_code_by_recip(c1, sc.e, sc.r)) |

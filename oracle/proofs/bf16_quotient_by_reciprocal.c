@@ -7,7 +7,12 @@
  * K2 computes them as ONE fp32 multiply by a per-row reciprocal and one rounding to bf16:
  *     n' = fl_bf16( fl_f32( d * ra ) ),  ra = RN_f32(1/a)        (__frcp_rn, once per row)
  *     u' = fl_bf16( fl_f32( c * rS ) ),  rS = RN_f32(1/S)
- * Claim: n' == n and u' == u, bit for bit, for EVERY bf16 a in the guarded window
+ * and SymQuantizer's dequantization (utils_quant.py:72) one more of the same kind:
+ *     y = fl_bf16( fl_f32( q / e ) )     q = rint(fl_bf16(x*s)): an integer that is a bf16 value,
+ *                                        e = fl_bf16(s + 1e-6)
+ *     y' = fl_bf16( fl_f32( q * re ) ),  re = RN_f32(1/e)
+ * (checked for every bf16 e in the window and every integer-valued bf16 q in [0, 512]).
+ * Claim: n' == n and u' == u (and y' == y), bit for bit, for EVERY bf16 a in the guarded window
  * [2^-100, 2^100] with every bf16 d in [0, a], and for every bits in 2..8 with every c.
  * Why it holds: d and a carry 8 significant bits, so d/a is either exactly
  * representable in bf16 or at least 2^-17 (relative) away from every bf16
@@ -87,6 +92,20 @@ int main(int argc, char** argv) {
       const uint16_t ref = bf16_rn(d / a);
       const uint16_t got = bf16_rn(d * ra);
       bad += ref != got;
+      ++total;
+    }
+  }
+  /* Sym dequantization: integer-valued bf16 codes 0..512 over every bf16 divisor in the window */
+#pragma omp parallel for reduction(+ : bad, total) schedule(dynamic, 64)
+  for (int eb = (27 << 7); eb < (228 << 7); ++eb) {
+    const float e = bf16_to_f((uint16_t)eb);
+    const float re = 1.0f / e;
+    for (int q = 0; q <= 512; ++q) {
+      const float qf = (float)q;
+      if (bf16_to_f(bf16_rn(qf)) != qf) continue;      /* not a bf16 value (odd numbers above 256) */
+      const float quo = qf / e;
+      if ((f2bits(quo) & 0x7f800000u) == 0x7f800000u) continue;
+      bad += bf16_rn(quo) != bf16_rn(qf * re);
       ++total;
     }
   }
