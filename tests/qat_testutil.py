@@ -76,3 +76,40 @@ def clip_cases(g):
             lo, hi = clip[4:].split("_")
             out.append((q, key, mode == "lw", float(lo), float(hi), k))
     return out
+
+
+def fuzz_cases(seed: int, n_cases: int = 6):
+    """Seeded random fake-quant cases shared by the CPU test that pins the oracle to the live
+    reference and the GPU test that pins the kernels to the oracle: 1-D..4-D shapes (widths
+    1..9000, odd ones included), Sym bits 2..16 / Asym bits 2..12, both dtypes, layerwise now
+    and then, magnitudes 1e-3..1e3, injected +-2.0 / zeros / -0.0 / an all-zero row and, in the
+    last case of a seed, one NaN or +-inf.  Yields (what, dtype, sym, bits, layerwise, x, g)."""
+    rng = np.random.default_rng(1000 + seed)
+    gen = torch.Generator().manual_seed(2000 + seed)
+    for case in range(n_cases):
+        dtype = ("fp32", "bf16")[int(rng.integers(2))]
+        nd = int(rng.integers(1, 5))
+        cols = int(rng.choice([1, 7, 8, 24, 100, 172, 256, 1000, 1023, 4096, int(rng.integers(1, 9000))]))
+        lead = [int(rng.integers(1, 5)) for _ in range(nd - 1)]
+        if nd == 4:   # reduction over the last two dims
+            shape = (lead[0], lead[1], int(rng.integers(1, 9)), max(1, cols // 8))
+        else:
+            shape = tuple(lead) + (cols,)
+        sym = bool(rng.integers(2))
+        bits = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 12, 16] if sym else [2, 3, 4, 5, 7, 8, 9, 12]))
+        lw = bool(rng.integers(5) == 0)
+        scale = float(10.0 ** rng.uniform(-3, 3))
+        x = torch.randn(*shape, generator=gen) * scale
+        flat = x.view(-1)
+        n = flat.numel()
+        flat[::13] = 0.0
+        if n > 4:
+            flat[1], flat[2], flat[3] = 2.0, -2.0, -0.0
+        if nd >= 2 and shape[-1] > 1 and not lw:
+            x.view(-1, shape[-1])[0] = 0.0
+        if case == n_cases - 1 and n > 16:
+            flat[int(rng.integers(n))] = (float("nan"), float("inf"), -float("inf"))[seed % 3]
+        x = x.to(DTYPES[dtype])
+        g = torch.randn(*shape, generator=gen).to(DTYPES[dtype])
+        what = (seed, case, dtype, shape, "sym" if sym else "asym", bits, lw, scale)
+        yield what, dtype, sym, bits, lw, x, g

@@ -201,6 +201,23 @@ def test_unaligned_and_noncontiguous_inputs():
         SymQuantizer.apply(torch.zeros(2, 3, 4, 8).cuda().transpose(1, 2), CLIP, 4, False)
 
 
+# --------------------------------------------------------------- seeded fuzz: shapes x bits x dtypes
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_forward_backward_bit_exact_vs_oracle(seed):
+    """qat_testutil.fuzz_cases: random shapes x bit widths x dtypes x edge values (also the bit
+    widths that leave the packed-bf16 and single-multiply fast paths): y and the STE gradient bit
+    for bit against the oracle, which tests/test_oracle.py pins to the live reference on the
+    very same cases."""
+    for what, dtype, sym, bits, lw, x, g in U.fuzz_cases(seed):
+        xi = x.cuda().requires_grad_(True)
+        y = _q("sym" if sym else "asym").apply(xi, CLIP, bits, lw)
+        y.backward(g.cuda())
+        ref = (qo.sym_forward if sym else qo.asym_forward)(U.tensor_to_f32(x), bits, lw, dtype)["y"]
+        assert qo.count_mismatch(U.tensor_to_f32(y), ref) == 0, what
+        gref = qo.ste_backward(U.tensor_to_f32(g), U.tensor_to_f32(x), -2.0, 2.0, dtype)["gx"]
+        assert qo.count_mismatch(U.tensor_to_f32(xi.grad), gref) == 0, what
+
+
 # --------------------------------------------------------------- config 5: LLaMA-13B shapes, 8 shards
 @pytest.mark.parametrize("shape,bits,what", [
     ((13824, 5120), 4, "gate/up_proj weight: sharded by output channel"),

@@ -191,3 +191,38 @@ def test_harness_layer_on_b200_matches_oracle_module(fused, monkeypatch):
     floor, mine = rel("ref", "grid"), rel("ref", "mine")
     for name, f, m in zip(names, floor, mine):
         assert m < 2 * f + 1e-2, (name, "product vs reference", m, "grid statement vs reference", f)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_linear_is_the_grid_statement_bit_for_bit(dtype):
+    """QuantizeLinear's fused path (K1 codes -> tcgen05 int8 GEMM -> dual-scale epilogue) against
+    oracle/grid_module.py on the GPU, random shapes and bit widths: the forward output must be
+    IDENTICAL (exact integer dot product, then the same two fp32 multiplies and one rounding);
+    gradients go through the same library GEMM on operands that are bit-identical."""
+    import llm_qat_b200
+
+    rng = np.random.default_rng(7)
+    gen = torch.Generator().manual_seed(7)
+    for case in range(10):
+        T = int(rng.choice([1, 5, 64, 200, 333, 1024]))
+        K = 16 * int(rng.integers(1, 90))
+        N = int(rng.choice([8, 24, 256, 264, 1000, 1376]))
+        w_bits, a_bits = int(rng.integers(3, 9)), int(rng.integers(3, 9))
+        x = (torch.randn(T, K, generator=gen) * float(10.0 ** rng.uniform(-1, 1))).to(dtype).cuda()
+        w = (torch.randn(N, K, generator=gen) * 0.05).to(dtype).cuda()
+        go = torch.randn(T, N, generator=gen).to(dtype).cuda()
+        res = []
+        for mod in (G, llm_qat_b200.utils_quant):
+            lin = mod.QuantizeLinear(K, N, w_bits=w_bits, a_bits=a_bits).to(dtype).cuda()
+            with torch.no_grad():
+                lin.weight.copy_(w)
+            xi = x.clone().requires_grad_(True)
+            out = lin(xi)
+            out.backward(go)
+            res.append((out, xi.grad, lin.weight.grad))
+        what = (case, T, K, N, w_bits, a_bits, dtype)
+        assert torch.equal(res[0][0], res[1][0]), what
+        for a, c in zip(res[0][1:], res[1][1:]):
+            rel = ((a.double() - c.double()).norm() / a.double().norm().clamp_min(1e-30)).item()
+            assert rel <= (1e-2 if dtype == torch.bfloat16 else 1e-5), what

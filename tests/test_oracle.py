@@ -138,3 +138,33 @@ def test_bf16_reciprocal_quotient_proof(tmp_path):
     for args in ([], ["addsub"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only exists in the build container")
+def test_oracle_fuzz_matches_live_reference():
+    """The oracle against the UNMODIFIED reference (imported read-only) on the seeded fuzz cases
+    the GPU parity test uses: forward values and STE gradients, bit for bit."""
+    import sys
+
+    import torch
+
+    sys.dont_write_bytecode = True
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import importlib
+
+    uq = importlib.import_module("models.utils_quant")
+    assert uq.__file__.startswith("/root/reference")
+    clip = torch.tensor([-2.0, 2.0])
+    n = 0
+    for seed in range(12):
+        for what, dtype, sym, bits, lw, x, g in U.fuzz_cases(seed):
+            xi = x.clone().requires_grad_(True)
+            y = (uq.SymQuantizer if sym else uq.AsymQuantizer).apply(xi, clip, bits, lw)
+            y.backward(g)
+            ref = (qo.sym_forward if sym else qo.asym_forward)(U.tensor_to_f32(x), bits, lw, dtype)["y"]
+            assert qo.count_mismatch(U.tensor_to_f32(y), ref) == 0, what
+            gref = qo.ste_backward(U.tensor_to_f32(g), U.tensor_to_f32(x), -2.0, 2.0, dtype)["gx"]
+            assert qo.count_mismatch(U.tensor_to_f32(xi.grad), gref) == 0, what
+            n += 1
+    assert n == 72
