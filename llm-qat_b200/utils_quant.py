@@ -17,14 +17,20 @@ Install under the reference's import name before its model file is imported::
     from models.modeling_llama_quant import LlamaForCausalLM
 
 Run-time knobs (environment; signatures stay the reference's):
-  QAT_B200_CACHE=0|1          memoise weight codes per module (until the parameter changes) and the
-                              last activation's codes per device (default 1).
+  QAT_B200_CACHE=0|1|2        1 (default): a module's weight codes are reused only by the checkpoint
+                              recompute of the SAME step (forward re-entered from inside a backward
+                              pass — weights cannot have changed), and q/k/v (gate/up) share the codes
+                              of their common input tensor.  2: weights are frozen (evaluation, gradient
+                              accumulation): also reuse across plain forwards, keyed on the parameter's
+                              (data_ptr, _version) — NOT safe under wrappers that rewrite parameter
+                              storage behind that key (FSDP use_orig_params=True).  0: no reuse.
   QAT_B200_FUSED_LINEAR=0|1   QuantizeLinear uses the integer-grid tcgen05 GEMM (default 1, taken
                               when shapes/dtypes allow) or the fake-quant kernels + F.linear (0).
 """
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -256,8 +262,17 @@ def _fused_linear_enabled() -> bool:
     return os.environ.get("QAT_B200_FUSED_LINEAR", "1") != "0"
 
 
-def _cache_enabled() -> bool:
-    return os.environ.get("QAT_B200_CACHE", "1") != "0"
+def _cache_mode() -> int:
+    v = os.environ.get("QAT_B200_CACHE", "1")
+    return 0 if v == "0" else 2 if v == "2" else 1
+
+
+def _in_backward_pass() -> bool:
+    """True while autograd is executing a backward graph on this thread — i.e. this
+    forward is a gradient-checkpoint recompute (torch.utils.checkpoint, reentrant or
+    not).  Parameters are only updated between backward passes, so codes produced by
+    the step's original forward are still those of the current weights."""
+    return torch._C._current_graph_task_id() != -1
 
 
 def _feed_layout(rows: int, cols: int):
@@ -277,9 +292,10 @@ def _feed_views(blob: torch.Tensor, rows: int, cols: int):
 
 
 # Single-slot memo of the last quantized activation per device: q/k/v (and gate/up)
-# receive the very same tensor, so its codes are produced once.
-# The slot holds a reference to the input, so its storage cannot be recycled
-# while the key (data_ptr, version, ...) is live.
+# receive the very same tensor OBJECT, so its codes are produced once (SURVEY.md
+# 8f-2).  A hit needs that identity (weak reference) plus an unchanged _version;
+# the slot also pins the detached view, so the storage cannot be recycled while
+# the entry is live.
 _ACT_SLOT: dict = {}
 
 
@@ -289,9 +305,8 @@ class _QuantLinearFn(torch.autograd.Function):
 
     forward : ONE C call: K1 codes-only passes (int8 codes + row divisors + packed
               STE masks) -> tcgen05 int8 GEMM with the dual-scale epilogue (K4).
-              The weight's codes are memoised on the module, keyed on the
-              parameter's (data_ptr, _version): they are rebuilt only after an
-              optimizer step, not on every forward / checkpoint recompute.
+              The weight's codes are kept on the module and reused by the
+              gradient-checkpoint recompute of the same step (see QAT_B200_CACHE).
     backward: dequantized operands are rebuilt from codes (q / e, bit-identical
               to the reference's fake-quant outputs); dgrad/wgrad are plain
               library GEMMs; the STE masks saved by the forward gate them.
@@ -313,16 +328,18 @@ class _QuantLinearFn(torch.autograd.Function):
         dev = x2.device
         dt = _DTYPES[x2.dtype]
         stream = _stream_ptr(dev)
-        use_cache = _cache_enabled()
+        mode = _cache_mode()
 
-        xkey = (x2.data_ptr(), x2._version, T, K, dt, a_bits, stream)
-        slot = _ACT_SLOT.get(dev.index) if use_cache else None
-        if slot is not None and slot[0] == xkey:
+        xkey = (x2.data_ptr(), input._version, T, K, dt, a_bits, stream)
+        slot = _ACT_SLOT.get(dev.index) if mode else None
+        if slot is not None and slot[0] == xkey and slot[3]() is input:
             xblob, reuse_x = slot[2], 1
         else:
             xblob, reuse_x = torch.empty(_feed_layout(T, K)[2], dtype=torch.uint8, device=dev), 0
         wkey = (w.data_ptr(), weight._version, N, K, dt, w_bits, stream)
-        cached = getattr(owner, "_qat_wfeed", None) if (use_cache and owner is not None) else None
+        cached = None
+        if owner is not None and (mode == 2 or (mode == 1 and _in_backward_pass())):
+            cached = getattr(owner, "_qat_wfeed", None)
         if cached is not None and cached[0] == wkey:
             wblob, reuse_w = cached[1], 1
         else:
@@ -338,8 +355,8 @@ class _QuantLinearFn(torch.autograd.Function):
                 T, N, K, dt, int(a_bits), int(w_bits), -2.0, 2.0,  # clip: utils_quant.py:198,245
                 reuse_x, reuse_w, stream)
         check(rc, "qat_qlinear_fused_fwd")
-        if use_cache:
-            _ACT_SLOT[dev.index] = (xkey, x2, xblob)
+        if mode:
+            _ACT_SLOT[dev.index] = (xkey, x2, xblob, weakref.ref(input))
             if owner is not None:
                 owner._qat_wfeed = (wkey, wblob)
         ctx.save_for_backward(xblob, wblob)

@@ -387,10 +387,13 @@ def _qlinear_exact_case(qlinear_i8, T, N, K, out_dtype):
 
 
 def test_quantize_linear_caches_are_transparent(monkeypatch):
-    """Weight codes are memoised per module until the parameter changes; the last
-    activation's codes are shared by consecutive layers fed the same tensor (q/k/v).
-    Neither may change a result."""
-    from llm_qat_b200 import QuantizeLinear
+    """QAT_B200_CACHE: 1 = weight codes reused only by the checkpoint recompute of the same step,
+    activation codes shared by consecutive layers fed the same tensor object (q/k/v); 2 = weight
+    codes also reused across plain forwards until the parameter's (data_ptr, _version) changes.
+    No mode may change a result (0 = no reuse is the baseline)."""
+    from torch.utils.checkpoint import checkpoint
+
+    from llm_qat_b200 import QuantizeLinear, _lib
 
     gen = torch.Generator().manual_seed(77)
     x = torch.randn(4, 50, 256, generator=gen).bfloat16().cuda()
@@ -401,30 +404,50 @@ def test_quantize_linear_caches_are_transparent(monkeypatch):
         monkeypatch.setenv("QAT_B200_CACHE", cache)
         monkeypatch.setenv("QAT_B200_FUSED_LINEAR", "1")
         lins = [QuantizeLinear(256, 384, w_bits=4, a_bits=8).bfloat16().cuda() for _ in range(3)]
-        res = []
+        res, launches = [], []
         for lin, w in zip(lins, ws):
             with torch.no_grad():
                 lin.weight.copy_(w)
         xi = x.clone().requires_grad_(True)
+        n0 = _lib.launch_count()
         outs = [lin(xi) for lin in lins]              # same input three times (q/k/v pattern)
+        launches.append(_lib.launch_count() - n0)     # 3 GEMMs + 3 weight quantizations + 1 or 3 activation ones
         sum(o.float().mul(go.float()).sum() for o in outs).backward()
         res += [o.detach().clone() for o in outs] + [xi.grad.clone()] + [lin.weight.grad.clone() for lin in lins]
-        # optimizer-style in-place update: the cached codes must be dropped
+        # optimizer-style in-place update: stale codes must never be used
         with torch.no_grad():
             lins[0].weight.mul_(-1.5)
         res.append(lins[0](xi).detach().clone())
-        res.append(lins[0](xi).detach().clone())       # second call hits the weight cache
+        n0 = _lib.launch_count()
+        res.append(lins[0](xi).detach().clone())       # plain second forward: reuses the weight codes in mode 2 only
+        launches.append(_lib.launch_count() - n0)
         # in-place change of the activation: the activation slot must miss
         with torch.no_grad():
             xi.mul_(0.5)
         res.append(lins[1](xi).detach().clone())
-        return res
+        # gradient checkpointing, both flavours: the recompute inside backward reuses the weight codes (modes 1, 2)
+        for reentrant in (False, True):
+            xc = x.clone().requires_grad_(True)
+            lins[2].weight.grad = None
+            y = checkpoint(lins[2], xc, use_reentrant=reentrant)
+            n0 = _lib.launch_count()
+            y.backward(go)
+            launches.append(_lib.launch_count() - n0)
+            res += [y.detach().clone(), xc.grad.clone(), lins[2].weight.grad.clone()]
+        return res, launches
 
-    a, b = run("1"), run("0")
-    assert len(a) == len(b)
-    for i, (u, v) in enumerate(zip(a, b)):
-        assert torch.equal(u, v), i
+    (a, la), (b, lb), (c, lc) = run("1"), run("0"), run("2")
+    assert len(a) == len(b) == len(c)
+    for i, (u, v, w) in enumerate(zip(a, b, c)):
+        assert torch.equal(u, v) and torch.equal(u, w), i
     assert torch.equal(a[7], a[8]) and not torch.equal(a[0], a[7])
+    # what was actually skipped: [q/k/v forward, plain second forward, backward incl. recompute x2]
+    assert lb[0] == 9 and la[0] == 7 and lc[0] == 7          # activation codes shared in modes 1 and 2
+    assert lb[1] == 3 and la[1] == 2 and lc[1] == 1          # plain re-forward: activation slot hits (1, 2); only mode 2 trusts the weight's version key
+    # recompute skips the weight quantization; the non-reentrant flavour re-enters with the very same
+    # input tensor object, so the activation slot hits too
+    assert la[2] == lb[2] - 2 and la[3] == lb[3] - 1
+    assert lc[2] == la[2] and lc[3] == la[3]
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
