@@ -37,6 +37,12 @@ extern "C" {
 /* element types of x / y / g / gx */
 #define QAT_F32 0
 #define QAT_BF16 1
+/* SymQuantizer on a bf16 tensor inside torch.autocast — the context HF's Trainer runs the step in
+ * (kd_trainer.py:106).  Autocast executes `Q / (max + 1e-6)` (Tensor.__rtruediv__ = reciprocal * Q)
+ * in fp32, so the reference's chain becomes: max|x| and `max + 1e-6` in bf16, then the reciprocal, the
+ * scale, x * s, round, s + 1e-6 and the division all in fp32, and the result is an fp32 tensor
+ * (measured on the GPU box: tests/gpu_autocast_probe.py).  qat_sym_fwd only: x bf16, y fp32. */
+#define QAT_BF16_AMP 2
 
 /* optional integer-code output */
 #define QAT_CODES_NONE 0

@@ -138,7 +138,7 @@ __device__ __forceinline__ void accumulate_scalar(RowStat& r, float f) {
 // bf16 Sym keeps two u16 lanes while accumulating; fold them into fp32 |x| bits
 template <int DT, bool SYM, bool VEC>
 __device__ __forceinline__ void finalize_thread_stat(RowStat& r) {
-  if (SYM && VEC && DT == QAT_BF16) {
+  if (SYM && VEC && DT != QAT_F32) {
     uint32_t m = max(r.amax_bits & 0xffffu, r.amax_bits >> 16);
     r.amax_bits = m << 16;
   }
@@ -190,19 +190,20 @@ __device__ __forceinline__ void emit_vec(const FwdParams& p, const Scale& sc, co
     for (int i = 0; i < N; ++i) yv[i] = sc.template apply<FAST>(vec_get<DT>(v, i), &qv[i]);
   }
   if (p.y != nullptr && valid) {
-    uint4 o;
-    if (DT == QAT_F32) {
-      o.x = __float_as_uint(yv[0]);
-      o.y = __float_as_uint(yv[1]);
-      o.z = __float_as_uint(yv[2]);
-      o.w = __float_as_uint(yv[3]);
+    char* dst = reinterpret_cast<char*>(p.y) + e0 * Num<DT>::kOutBytes;
+    if (Num<DT>::kOutBytes == 4) {
+#pragma unroll
+      for (int k = 0; k < N / 4; ++k)   // one store for fp32 input, two for bf16 input with fp32 y
+        stg_stream(dst + 16 * k, make_uint4(__float_as_uint(yv[4 * k]), __float_as_uint(yv[4 * k + 1]),
+                                            __float_as_uint(yv[4 * k + 2]), __float_as_uint(yv[4 * k + 3])));
     } else {
+      uint4 o;
       o.x = pack_bf16x2(yv[0], yv[1]);
       o.y = pack_bf16x2(yv[2 % N], yv[3 % N]);
       o.z = pack_bf16x2(yv[4 % N], yv[5 % N]);
       o.w = pack_bf16x2(yv[6 % N], yv[7 % N]);
+      stg_stream(dst, o);
     }
-    stg_stream(reinterpret_cast<char*>(p.y) + e0 * Num<DT>::kBytes, o);
   }
   if (p.codes != nullptr && valid) {
     if (p.codes_kind == QAT_CODES_I8) {
@@ -256,7 +257,7 @@ __device__ __forceinline__ void emit_scalar(const FwdParams& p, const Scale& sc,
   float q;
   float yf = sc.template apply<FAST>(xf, &q);
   if (p.y != nullptr) {
-    if (DT == QAT_F32)
+    if (Num<DT>::kOutBytes == 4)
       reinterpret_cast<float*>(p.y)[e0] = yf;
     else
       reinterpret_cast<__nv_bfloat16*>(p.y)[e0] = __float2bfloat16_rn(yf);
@@ -334,8 +335,10 @@ __device__ __forceinline__ typename ScaleOf<DT, SYM>::type warp_derive_scale(con
 }
 
 // y for one 16-byte vector, no side outputs (the Quantizer.apply hot loop)
+// o[0] (and o[1] when y elements are twice as wide as x elements) receive the output vectors
 template <int DT, bool SYM, bool FAST, typename Scale>
-__device__ __forceinline__ uint4 quant_vec_y(const Scale& sc, const uint4& v) {
+__device__ __forceinline__ void quant_vec_y(const Scale& sc, const uint4& v,
+                                            uint4 (&oo)[Num<DT>::kOutBytes / Num<DT>::kBytes]) {
   uint4 o;
   if constexpr (SYM && DT == QAT_BF16) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -365,15 +368,19 @@ __device__ __forceinline__ uint4 quant_vec_y(const Scale& sc, const uint4& v) {
     float yv[N], q;
 #pragma unroll
     for (int i = 0; i < N; ++i) yv[i] = sc.template apply<FAST>(vec_get<DT>(v, i), &q);
-    if (DT == QAT_F32) {
-      o = make_uint4(__float_as_uint(yv[0]), __float_as_uint(yv[1]), __float_as_uint(yv[2]),
-                     __float_as_uint(yv[3]));
+    if (Num<DT>::kOutBytes == 4) {
+#pragma unroll
+      for (int k = 0; k < N / 4; ++k)
+        oo[k % (Num<DT>::kOutBytes / Num<DT>::kBytes)] =
+            make_uint4(__float_as_uint(yv[4 * k]), __float_as_uint(yv[4 * k + 1]), __float_as_uint(yv[4 * k + 2]),
+                       __float_as_uint(yv[4 * k + 3]));
+      return;
     } else {
       o = make_uint4(pack_bf16x2(yv[0], yv[1]), pack_bf16x2(yv[2 % N], yv[3 % N]),
                      pack_bf16x2(yv[4 % N], yv[5 % N]), pack_bf16x2(yv[6 % N], yv[7 % N]));
     }
   }
-  return o;
+  oo[0] = o;
 }
 
 // int8 codes (+ optional packed mask) for one vector: the GEMM feed.  Only the
@@ -471,21 +478,30 @@ __global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
   }
 
   if constexpr (OUT == OUT_Y) {
-    uint4* yrow = reinterpret_cast<uint4*>(p.y) + row * p.nvec;
+    constexpr int OV = Num<DT>::kOutBytes / Num<DT>::kBytes;  // output vectors per input vector
+    uint4* yrow = reinterpret_cast<uint4*>(p.y) + row * p.nvec * OV;
     asm volatile("" : "+l"(yrow));
     if (sc.fast) {  // row-uniform => warp-uniform: a warp never spans two rows
 #pragma unroll
       for (int i = 0; i < ITERS; ++i) {
         const uint32_t j = t + (uint32_t)i * group;
-        const uint4 o = quant_vec_y<DT, SYM, true>(sc, v[i]);
-        if (j < nvec) stg_stream(yrow + j, o);
+        uint4 o[OV];
+        quant_vec_y<DT, SYM, true>(sc, v[i], o);
+        if (j < nvec) {
+#pragma unroll
+          for (int k = 0; k < OV; ++k) stg_stream(yrow + j * OV + k, o[k]);
+        }
       }
     } else {
 #pragma unroll
       for (int i = 0; i < ITERS; ++i) {
         const uint32_t j = t + (uint32_t)i * group;
-        const uint4 o = quant_vec_y<DT, SYM, false>(sc, v[i]);
-        if (j < nvec) stg_stream(yrow + j, o);
+        uint4 o[OV];
+        quant_vec_y<DT, SYM, false>(sc, v[i], o);
+        if (j < nvec) {
+#pragma unroll
+          for (int k = 0; k < OV; ++k) stg_stream(yrow + j * OV + k, o[k]);
+        }
       }
     }
   } else if constexpr (OUT == OUT_FEED) {
@@ -811,7 +827,8 @@ template <bool SYM>
 int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, float* st1,
               uint8_t* mask, float lo, float hi, int64_t rows, int64_t cols, int dtype, int bits,
               void* workspace, size_t workspace_bytes, void* stream) {
-  QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16, "dtype must be QAT_F32 or QAT_BF16 (got %d)", dtype);
+  QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16 || (SYM && dtype == QAT_BF16_AMP),
+                "dtype must be QAT_F32, QAT_BF16 or (Sym only) QAT_BF16_AMP (got %d)", dtype);
   QAT_CHECK_ARG(rows >= 0 && cols >= 0, "negative shape [%lld, %lld]", (long long)rows, (long long)cols);
   QAT_CHECK_ARG(SYM ? (bits >= 2 && bits <= 16) : (bits >= 1 && bits <= 15),
                 "unsupported num_bits %d", bits);
@@ -872,6 +889,9 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == QAT_F32) return dispatch<QAT_F32, SYM>(p, pl, st);
+  if constexpr (SYM) {
+    if (dtype == QAT_BF16_AMP) return dispatch<QAT_BF16_AMP, true>(p, pl, st);
+  }
   return dispatch<QAT_BF16, SYM>(p, pl, st);
 }
 

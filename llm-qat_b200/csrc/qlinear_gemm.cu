@@ -491,12 +491,15 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box
 template <int OUT_DT, int CG>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   using C = Cfg<CG>;
-  static bool attr_set = false;  // per instantiation; benign race (idempotent)
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
+  static bool attr_set[64] = {};  // per instantiation; benign race (idempotent)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(qlinear_i8_kernel<OUT_DT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qlinear_i8_kernel)");
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int tiles = p.m_blocks * p.n_blocks;
   int units = num_sms() / CG;   // one CTA (pair) per SM (TPC)
@@ -599,5 +602,6 @@ extern "C" int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, in
                          nullptr, 0, stream);
     if (rc != QAT_OK) return rc;
   }
-  return qat_qlinear_i8_fwd(qx, qw, ex, ew, out, T, N, K, dtype, stream);
+  // under autocast the reference's F.linear runs, and returns, bf16
+  return qat_qlinear_i8_fwd(qx, qw, ex, ew, out, T, N, K, dtype == QAT_BF16_AMP ? QAT_BF16 : dtype, stream);
 }

@@ -36,7 +36,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import CODES_I8, CODES_I16, CODES_NONE, QAT_BF16, QAT_F32, check
+from ._lib import CODES_I8, CODES_I16, CODES_NONE, QAT_BF16, QAT_BF16_AMP, QAT_F32, check
 
 __all__ = ["SymQuantizer", "AsymQuantizer", "QuantizeLinear"]
 
@@ -56,6 +56,15 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         raise RuntimeError(
             f"{what}: expected a CUDA tensor, got device {t.device}. "
             "llm-qat_b200 runs only on B200 (sm_100a); there is no CPU fallback.")
+
+
+def _sym_amp(t: torch.Tensor) -> bool:
+    """SymQuantizer on a bf16 CUDA tensor inside torch.autocast (HF's Trainer runs the step in one,
+    kd_trainer.py:106): autocast executes the reference's `Q / (max + 1e-6)` — a reciprocal — in fp32,
+    so everything after it is fp32 and the fake-quantized tensor comes back as float32
+    (tests/gpu_autocast_probe.py).  The kernels reproduce that chain as dtype QAT_BF16_AMP.
+    AsymQuantizer contains no op autocast touches and is unchanged."""
+    return t.dtype == torch.bfloat16 and t.is_cuda and torch.is_autocast_enabled("cuda")
 
 
 def _stream_ptr(device) -> int:
@@ -113,7 +122,7 @@ def _reduction_view(input: torch.Tensor, layerwise: bool):
 
 def fake_quant_forward(input: torch.Tensor, num_bits: int, layerwise: bool, symmetric: bool, *,
                        want_y: bool = True, codes_kind: int = CODES_NONE, want_scales: bool = False,
-                       mask_clip=None):
+                       mask_clip=None, amp: bool = False):
     """One launch of K1/K2 (or the two-phase K5 for long rows).
 
     Returns ``(y, codes, st0, st1, mask)``; entries not requested are ``None``.
@@ -121,6 +130,10 @@ def fake_quant_forward(input: torch.Tensor, num_bits: int, layerwise: bool, symm
     """
     _require_cuda(input, "fake-quant forward")
     dt = _dtype_code(input)
+    if amp:
+        if not (symmetric and dt == QAT_BF16):
+            raise TypeError("the autocast variant exists for SymQuantizer on bfloat16 tensors only")
+        dt = QAT_BF16_AMP
     rows, cols = _reduction_view(input, layerwise)
     if input.numel() == 0:
         raise RuntimeError("fake-quant of an empty tensor (the reference's max() raises too)")
@@ -128,7 +141,7 @@ def fake_quant_forward(input: torch.Tensor, num_bits: int, layerwise: bool, symm
     if not x.is_contiguous():
         x = x.contiguous()
     dev = x.device
-    y = torch.empty_like(x) if want_y else None
+    y = (torch.empty(x.shape, dtype=torch.float32, device=dev) if amp else torch.empty_like(x)) if want_y else None
     codes = None
     if codes_kind == CODES_I8:
         codes = torch.empty(x.shape, dtype=torch.int8 if symmetric else torch.uint8, device=dev)
@@ -207,12 +220,17 @@ class SymQuantizer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, clip_val, num_bits, layerwise):
         ctx.save_for_backward(input, clip_val)
-        y, *_ = fake_quant_forward(input, num_bits, layerwise, symmetric=True)
+        y, *_ = fake_quant_forward(input, num_bits, layerwise, symmetric=True, amp=_sym_amp(input))
         return y
 
     @staticmethod
     def backward(ctx, grad_output):
         input, clip_val = ctx.saved_tensors
+        if grad_output.dtype != input.dtype:
+            # autocast variant: y (and its gradient) are fp32 while the input is bf16; the reference
+            # masks the fp32 gradient and the autograd engine then casts it to the input's dtype —
+            # casting first gives the same bits
+            grad_output = grad_output.to(input.dtype)
         return ste_backward(grad_output, input, clip_val), None, None, None
 
 
@@ -326,7 +344,7 @@ class _QuantLinearFn(torch.autograd.Function):
             w = w.contiguous()
         T = x2.numel() // K
         dev = x2.device
-        dt = _DTYPES[x2.dtype]
+        dt = QAT_BF16_AMP if _sym_amp(x2) else _DTYPES[x2.dtype]   # codes from the autocast chain under autocast
         stream = _stream_ptr(dev)
         mode = _cache_mode()
 
@@ -462,6 +480,9 @@ class QuantizeLinear(nn.Linear):
             and 1 <= input_.dim() <= 3
             and input_.shape[-1] % 16 == 0
             and input_.numel() > 0
+            # under autocast to another dtype the reference's F.linear casts its operands and
+            # returns that dtype: leave that case to the unfused path, which does exactly that
+            and not (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") != input_.dtype)
         )
 
     def forward(self, input_):

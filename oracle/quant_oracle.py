@@ -104,14 +104,23 @@ def _nanmax(a: np.ndarray) -> np.ndarray:
 # SymQuantizer.forward  (utils_quant.py:37-74)
 # --------------------------------------------------------------------------
 def sym_forward(x: np.ndarray, num_bits: int, layerwise: bool = False, dtype: str = "fp32"):
-    """Returns dict(y, codes, s, e) — y has x's shape; s, e are per-row [rows]."""
-    fl = _fl(dtype)
+    """Returns dict(y, codes, s, e) — y has x's shape; s, e are per-row [rows].
+
+    dtype "bf16_amp": a bf16 tensor inside torch.autocast (what HF's Trainer wraps the step in,
+    kd_trainer.py:106).  Autocast runs `reciprocal` in fp32, so `max + 1e-6` is still a bf16 op
+    and everything after it — reciprocal, * Q, x * s (bf16 x fp32 promotes), round, s + 1e-6,
+    the division — is fp32; y is a float32 tensor.  Pinned on the GPU against the restated
+    chain run under the same autocast context (tests/test_gpu_parity.py)."""
+    amp = dtype == "bf16_amp"
+    fl = _fl("fp32" if amp else dtype)
     x = np.asarray(x, dtype=F32)
     x2 = as_rows(x, layerwise)
     Q = F32(2 ** (num_bits - 1) - 1)
     with np.errstate(all="ignore"):
         m = _nanmax(np.abs(x2))              # :51 / :56 / :63  (exact)
         d = fl(m + EPS_SYM)                  # :71  max_input + 1e-6
+        if amp:
+            d = bf16_round(d)
         r = fl(F32(1.0) / d)                 # :71  Q / d  ==  d.reciprocal() * Q
         s = fl(r * Q)
         p = fl(x2 * s)                       # :72  input * s

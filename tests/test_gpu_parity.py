@@ -450,6 +450,73 @@ def test_quantize_linear_caches_are_transparent(monkeypatch):
     assert lc[2] == la[2] and lc[3] == la[3]
 
 
+@pytest.mark.parametrize("bits", [4, 8])
+def test_sym_quantizer_under_autocast_is_the_fp32_scale_chain(bits):
+    """Inside torch.autocast the reference's SymQuantizer on a bf16 tensor computes its scale in
+    fp32 and returns float32 (autocast runs `reciprocal` in fp32).  Product == the restated chain
+    under the same context == the numpy oracle's "bf16_amp" mode, bit for bit: forward values,
+    codes / divisors / mask of the GEMM feed, and the gradient (which autograd casts to bf16)."""
+    from llm_qat_b200 import SymQuantizer
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.utils_quant import fake_quant_forward
+    from oracle import ref_module as R
+
+    gen = torch.Generator().manual_seed(40 + bits)
+    for shape in ((64, 4096), (3, 17, 1000), (5, 11008), (7, 172), (2, 3, 4, 24)):
+        x = (torch.randn(*shape, generator=gen) * 0.8).bfloat16()
+        x.view(-1)[:4] = torch.tensor([2.0, -2.0, 0.0, -0.0]).bfloat16()
+        g = torch.randn(*shape, generator=gen)
+        outs = []
+        for Q in (R.SymQuantizer, SymQuantizer):
+            xi = x.cuda().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = Q.apply(xi, CLIP, bits, False)
+            assert y.dtype == torch.float32
+            y.backward(g.cuda())
+            assert xi.grad.dtype == torch.bfloat16
+            outs.append((y.detach().cpu(), xi.grad.cpu()))
+        assert torch.equal(outs[0][0].view(torch.int32), outs[1][0].view(torch.int32)), shape
+        assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16)), shape
+        o = qo.sym_forward(U.tensor_to_f32(x), bits, False, "bf16_amp")
+        assert qo.count_mismatch(outs[1][0].numpy(), o["y"]) == 0, shape
+        if len(shape) == 2 and shape[1] % 16 == 0:
+            _, codes, _, e, _ = fake_quant_forward(x.cuda(), bits, False, True, want_y=False, codes_kind=CODES_I8,
+                                                   want_scales=True, mask_clip=(-2.0, 2.0), amp=True)
+            assert np.array_equal(codes.cpu().numpy().astype(np.float32), o["codes"])
+            assert qo.count_mismatch(e.cpu().numpy(), o["e"]) == 0
+
+
+def test_quantize_linear_under_autocast_matches_reference_semantics():
+    """HF's Trainer wraps the step in torch.autocast(bf16) (kd_trainer.py:106).  With fp32 modules the
+    reference fake-quantizes in fp32 and its F.linear then runs — and returns — bf16; with bf16 modules
+    autocast is a no-op.  The product must give the same dtypes and values in both cases."""
+    from llm_qat_b200 import QuantizeLinear
+    from oracle import ref_module as R
+
+    gen = torch.Generator().manual_seed(3)
+    x32 = torch.randn(6, 40, 256, generator=gen).cuda()
+    w32 = (torch.randn(128, 256, generator=gen) * 0.05).cuda()
+    go = torch.randn(6, 40, 128, generator=gen).cuda()
+    for dtype in (torch.float32, torch.bfloat16):
+        res = []
+        for mod in (R, None):
+            lin = (mod.QuantizeLinear if mod else QuantizeLinear)(256, 128, w_bits=4, a_bits=8).to(dtype).cuda()
+            with torch.no_grad():
+                lin.weight.copy_(w32.to(dtype))
+            xi = x32.detach().clone().to(dtype).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = lin(xi)
+            out.backward(go.to(out.dtype))
+            res.append((out, xi.grad, lin.weight.grad))
+        (o_ref, dx_ref, dw_ref), (o, dx, dw) = res
+        assert o.dtype == o_ref.dtype == torch.bfloat16 and dx.dtype == dtype and dw.dtype == dtype
+        for a, c in ((o_ref, o), (dx_ref, dx), (dw_ref, dw)):
+            rel = ((a.double() - c.double()).norm() / a.double().norm()).item()
+            assert rel <= 1e-2, (dtype, rel)
+        if dtype == torch.float32:      # unfused under autocast: the very same op chain as the reference
+            assert torch.equal(o_ref, o)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_dequant_codes_reproduces_forward_output(dtype):
     from llm_qat_b200._lib import CODES_I8
