@@ -482,7 +482,8 @@ def run_b200(args):
             torch.cuda.empty_cache()
             torch.cuda.reset_peak_memory_stats()
             r = QB.time_qat_step(llm_qat_b200.utils_quant, cfg7, seq=2048, bsz=1, warmup=2,
-                                 steps=max(3, min(K, 5)), device=device, rank=rank, world=world)
+                                 steps=max(3, min(K, 5)), device=device, rank=rank, world=world,
+                                 autocast=True)   # the recipe: HF's Trainer runs the step in autocast(bf16)
             ms = r["ms_per_step"]
             if dist is not None:
                 t = torch.tensor([ms], device=device)
@@ -491,7 +492,7 @@ def run_b200(args):
             qat = dict(r, ms_per_step=round(ms, 2), tokens_per_s=round(world * 2048 / ms * 1e3), n_gpus=world,
                        model=("LLaMA-13B dims, random init, student W4A8KV8" if args.qat_model == "13b" else
                               "LLaMA-7B dims, random init, student W4A8KV4") + " + frozen FP teacher, KD (KL batchmean), "
-                             "grad checkpointing, AdamW, bf16" + (", DDP/NCCL all-reduce" if world > 1 else ""))
+                             "grad checkpointing, AdamW, bf16 inside torch.autocast(bf16) as kd_trainer.py:106 does" + (", DDP/NCCL all-reduce" if world > 1 else ""))
         except Exception as e:  # keep the headline line even if the big model cannot run
             qat = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.synchronize()

@@ -12,6 +12,7 @@ harness; tests/test_harness.py checks it against the real reference layer here.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass
 
@@ -205,12 +206,16 @@ def kd_loss(student_logits, teacher_logits):
     return F.kl_div(F.log_softmax(student_logits, dim=2), F.softmax(teacher_logits, dim=2), reduction="batchmean")
 
 
-def qat_step(student, teacher, input_ids, optimizer, kd_loss_scale=1.0):
-    """One training step of compute_loss_train + backward + optimizer (kd_trainer.py:53-127)."""
-    with torch.no_grad():
-        t_logits = teacher(input_ids)
-    s_logits = student(input_ids)
-    loss = kd_loss_scale * kd_loss(s_logits, t_logits)
+def qat_step(student, teacher, input_ids, optimizer, kd_loss_scale=1.0, autocast=False):
+    """One training step of compute_loss_train + backward + optimizer (kd_trainer.py:53-127).
+    ``autocast=True`` mirrors the recipe: HF's Trainer (run_train.sh `--bf16 True`) computes the
+    loss — teacher and student forward — inside torch.autocast(bfloat16) (kd_trainer.py:106)."""
+    ctx = torch.autocast(input_ids.device.type, dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+    with ctx:
+        with torch.no_grad():
+            t_logits = teacher(input_ids)
+        s_logits = student(input_ids)
+        loss = kd_loss_scale * kd_loss(s_logits, t_logits)
     del t_logits, s_logits
     loss.backward()
     optimizer.step()

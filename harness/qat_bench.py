@@ -4,6 +4,7 @@ bench.py passes the product (llm_qat_b200.utils_quant); tests/gpu_layer_bench.py
 also passes the oracle module to time the reference's eager GPU path."""
 from __future__ import annotations
 
+import contextlib
 import statistics
 
 import torch
@@ -26,7 +27,8 @@ def _timed(fn, warmup, steps):
     return times
 
 
-def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, device="cuda", seed=1234):
+def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, device="cuda", seed=1234,
+               autocast=False):
     """Config 3: one LlamaDecoderLayer W4A8KV4 bf16, hidden_states [bsz, seq, H], fwd + bwd."""
     torch.manual_seed(0)
     layer = H.DecoderLayer(cfg, quant).bfloat16().to(device)
@@ -41,19 +43,21 @@ def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, dev
     pos = torch.arange(seq, device=device)[None].expand(bsz, seq)
 
     def step():
-        y = layer(x, mask, pos)
-        y.backward(go)
+        with (torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()):
+            y = layer(x, mask, pos)
+        y.backward(go.to(y.dtype))
         x.grad = None
         for p in layer.parameters():
             p.grad = None
 
     t = _timed(step, warmup, steps)
     ms = statistics.median(t)
-    return {"ms_fwd_bwd": round(ms, 3), "tokens_per_s": round(bsz * seq / ms * 1e3), "seq": seq, "bsz": bsz}
+    return {"ms_fwd_bwd": round(ms, 3), "tokens_per_s": round(bsz * seq / ms * 1e3), "seq": seq, "bsz": bsz,
+            "autocast": autocast}
 
 
 def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=2, steps=5, device="cuda", rank=0, world=1,
-                  lr=2e-5):
+                  lr=2e-5, autocast=False):
     """Config 4/5: student (quantized) + frozen FP teacher of identical init, KD loss,
     gradient checkpointing, AdamW; DDP (NCCL all-reduce of the gradients) when world > 1.
     Returns this rank's median step time; the caller reduces max over ranks."""
@@ -73,7 +77,7 @@ def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=2, steps=5, d
     ids = torch.randint(0, cfg.vocab_size, (bsz, seq), generator=g).to(device)
 
     def step():
-        H.qat_step(model, teacher, ids, opt)
+        H.qat_step(model, teacher, ids, opt, autocast=autocast)
 
     t = _timed(step, warmup, steps)
     ms = statistics.median(t)
@@ -81,4 +85,4 @@ def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=2, steps=5, d
     del opt, model, student, teacher
     torch.cuda.empty_cache()
     return {"ms_per_step": round(ms, 2), "tokens_per_s_per_gpu": round(bsz * seq / ms * 1e3), "seq": seq,
-            "bsz_per_gpu": bsz, "peak_mem_GiB": round(mem, 1), "layers": cfg.num_hidden_layers}
+            "bsz_per_gpu": bsz, "peak_mem_GiB": round(mem, 1), "layers": cfg.num_hidden_layers, "autocast": autocast}

@@ -20,7 +20,7 @@ def main():
 
     layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     cfg = H.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4)
-    out = {"config3_layer": {}, "config4_step": {}}
+    out = {"config3_layer": {}, "config4_step": {}, "config3_layer_autocast": {}, "config4_step_autocast": {}}
     for name, quant, env in (("reference_eager_gpu", R, None), ("b200_unfused", llm_qat_b200.utils_quant, "0"),
                              ("b200_fused", llm_qat_b200.utils_quant, "1")):
         if env is not None:
@@ -35,6 +35,15 @@ def main():
         torch.cuda.reset_peak_memory_stats()
         out["config4_step"][name] = B.time_qat_step(quant, cfg4)
         print("config4", name, out["config4_step"][name], flush=True)
+    # the recipe's context: HF's Trainer runs the step inside torch.autocast(bf16) (kd_trainer.py:106)
+    for name, quant, env in (("reference_eager_gpu", R, None), ("b200_fused", llm_qat_b200.utils_quant, "1")):
+        if env is not None:
+            os.environ["QAT_B200_FUSED_LINEAR"] = env
+        out["config3_layer_autocast"][name] = B.time_layer(quant, cfg, autocast=True)
+        print("config3 autocast", name, out["config3_layer_autocast"][name], flush=True)
+        torch.cuda.reset_peak_memory_stats()
+        out["config4_step_autocast"][name] = B.time_qat_step(quant, cfg4, autocast=True)
+        print("config4 autocast", name, out["config4_step_autocast"][name], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "layer_bench.json"), "w"), indent=1)
 
