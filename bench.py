@@ -265,6 +265,36 @@ def time_shape_sweep(device, steps, pk):
                                  "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}
                 out[f"{dt_name}[{rows},{cols}] {qname}"] = res
             del xs, gs, ys, ds
+    # SymQuantizer inside torch.autocast: bf16 in, fp32 y (6 B/elem), and the GEMM feed (codes + mask: 3.125 B/elem)
+    for rows, cols in ((8192, 4096), (11008, 4096), (2048, 4096)):
+        n = rows * cols
+        nbuf = max(2, -(-300_000_000 // (n * 6)))
+        xs = [(torch.randn(rows, cols, generator=g) * 0.5).bfloat16().to(device) for _ in range(2)]
+        xs += [xs[i % 2].clone() for i in range(nbuf - 2)]
+        ys = [torch.empty(rows, cols, dtype=torch.float32, device=device) for _ in range(nbuf)]
+        cs = [torch.empty(rows, cols, dtype=torch.int8, device=device) for _ in range(nbuf)]
+        ms = [torch.empty(n // 8, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+        es = torch.empty(rows, dtype=torch.float32, device=device)
+        for mode, nbytes in (("y_fp32", n * 6), ("feed", n * 3 + n // 8)):
+            def once(i):
+                if mode == "y_fp32":
+                    rc = L.qat_sym_fwd(xs[i].data_ptr(), ys[i].data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, rows, cols, 2, 8, 0, 0, st)
+                else:
+                    rc = L.qat_sym_fwd(xs[i].data_ptr(), 0, cs[i].data_ptr(), 1, 0, es.data_ptr(), ms[i].data_ptr(),
+                                       -2.0, 2.0, rows, cols, 2, 8, 0, 0, st)
+                _lib.check(rc)
+            for i in range(nbuf):
+                once(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(steps):
+                once(k % nbuf)
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) / steps * 1e3
+            out[f"bf16_amp[{rows},{cols}] sym8 {mode}"] = {"fwd": {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                                                                  "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}}
+        del xs, ys, cs, ms
     return out
 
 

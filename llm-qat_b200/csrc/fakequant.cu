@@ -209,10 +209,7 @@ __device__ __forceinline__ void emit_vec(const FwdParams& p, const Scale& sc, co
     if (p.codes_kind == QAT_CODES_I8) {
       uint32_t w[N / 4];
 #pragma unroll
-      for (int i = 0; i < N / 4; ++i)
-        w[i] = (uint32_t)code_i8<SYM>(qv[4 * i]) | ((uint32_t)code_i8<SYM>(qv[4 * i + 1]) << 8) |
-               ((uint32_t)code_i8<SYM>(qv[4 * i + 2]) << 16) |
-               ((uint32_t)code_i8<SYM>(qv[4 * i + 3]) << 24);
+      for (int i = 0; i < N / 4; ++i) w[i] = pack_codes4<SYM>(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
       uint8_t* dst = reinterpret_cast<uint8_t*>(p.codes) + e0;
       if (N == 4) {
         *reinterpret_cast<uint32_t*>(dst) = w[0];
@@ -394,14 +391,14 @@ __device__ __forceinline__ void quant_vec_feed(const FwdParams& p, const Scale& 
   if constexpr (SYM && DT == QAT_BF16) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k) {   // p = fl_bf16(x*s); pack_codes4 rounds it half-to-even
       const uint32_t pw = mul_bf16x2(w[k], sc.s2);
-      qv[(2 * k) % N] = rintf(bf16lo(pw));
-      qv[(2 * k + 1) % N] = rintf(bf16hi(pw));
+      qv[(2 * k) % N] = bf16lo(pw);
+      qv[(2 * k + 1) % N] = bf16hi(pw);
     }
   } else if constexpr (SYM) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) qv[i] = rintf(Num<DT>::fl(__fmul_rn(vec_get<DT>(v, i), sc.s)));
+    for (int i = 0; i < N; ++i) qv[i] = Num<DT>::fl(__fmul_rn(vec_get<DT>(v, i), sc.s));
   } else if (DT == QAT_BF16 && FAST && sc_packed(sc)) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -412,9 +409,7 @@ __device__ __forceinline__ void quant_vec_feed(const FwdParams& p, const Scale& 
   }
   uint32_t cw[N / 4];
 #pragma unroll
-  for (int i = 0; i < N / 4; ++i)
-    cw[i] = (uint32_t)code_i8<SYM>(qv[4 * i]) | ((uint32_t)code_i8<SYM>(qv[4 * i + 1]) << 8) |
-            ((uint32_t)code_i8<SYM>(qv[4 * i + 2]) << 16) | ((uint32_t)code_i8<SYM>(qv[4 * i + 3]) << 24);
+  for (int i = 0; i < N / 4; ++i) cw[i] = pack_codes4<SYM>(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
   if (valid) {
     if (N == 4)
       *reinterpret_cast<uint32_t*>(codes_row + (size_t)j * N) = cw[0];
