@@ -102,8 +102,10 @@ class Attention(nn.Module):
         k = k.view(b, s, self.n_heads, self.head_dim).transpose(1, 2)
         v = v.view(b, s, self.n_heads, self.head_dim).transpose(1, 2)
         cos, sin = _rope_tables(self.head_dim, max(self.max_pos, s), h.device)
-        cos = cos.to(q.dtype)[position_ids].unsqueeze(1)
-        sin = sin.to(q.dtype)[position_ids].unsqueeze(1)
+        # rotary_emb(value_states, ...) returns tables in V's dtype (:334) — fp32 under autocast, where
+        # the K/V fake-quant returns float32
+        cos = cos.to(v.dtype)[position_ids].unsqueeze(1)
+        sin = sin.to(v.dtype)[position_ids].unsqueeze(1)
         q = q * cos + _rotate_half(q) * sin
         k = k * cos + _rotate_half(k) * sin
         w = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(self.head_dim)

@@ -378,6 +378,7 @@ class _QuantLinearFn(torch.autograd.Function):
             if owner is not None:
                 owner._qat_wfeed = (wkey, wblob)
         ctx.save_for_backward(xblob, wblob)
+        ctx.owner_ref = weakref.ref(owner) if (owner is not None and mode == 1) else None
         ctx.dims = (T, N, K)
         ctx.in_shape = input.shape
         ctx.dtype = input.dtype
@@ -416,6 +417,12 @@ class _QuantLinearFn(torch.autograd.Function):
                 gw = torch.empty_like(t)
                 check(L.qat_ste_bwd_from_mask(t.data_ptr(), wb + wm, gw.data_ptr(), N * K, dt, stream),
                       "qat_ste_bwd_from_mask")
+        # mode 1 keeps a module's codes only from its forward to its backward (for the checkpoint
+        # recompute in between): 1.125 B per weight element must not sit in HBM through the
+        # optimizer step
+        owner = ctx.owner_ref() if ctx.owner_ref is not None else None
+        if owner is not None:
+            owner._qat_wfeed = None
         return gx, gw, None, None, None
 
 

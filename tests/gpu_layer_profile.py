@@ -3,6 +3,8 @@
 torch.profiler kernel table for the product (fused) and the reference eager path."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import faulthandler
+faulthandler.dump_traceback_later(int(os.environ.get('PROFILE_TOOL_TIMEOUT', '240')), exit=True)   # a stuck run reports where
 import torch
 from torch.profiler import profile, ProfilerActivity
 from harness import llama_qat as H
@@ -11,6 +13,8 @@ import llm_qat_b200
 
 cfg = H.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4)
 seq, bsz = 2048, 1
+AUTOCAST = len(sys.argv) > 1 and sys.argv[1] == "autocast"   # the recipe's context (kd_trainer.py:106)
+import contextlib
 for name, quant in (("b200_fused", llm_qat_b200.utils_quant), ("reference_eager", R)):
     torch.manual_seed(0)
     layer = H.DecoderLayer(cfg, quant).bfloat16().cuda()
@@ -19,7 +23,9 @@ for name, quant in (("b200_fused", llm_qat_b200.utils_quant), ("reference_eager"
     mask = H.causal_mask(bsz, seq, torch.bfloat16, "cuda")
     pos = torch.arange(seq, device="cuda")[None].expand(bsz, seq)
     def step():
-        y = layer(x, mask, pos); y.backward(go); x.grad = None
+        with (torch.autocast("cuda", dtype=torch.bfloat16) if AUTOCAST else contextlib.nullcontext()):
+            y = layer(x, mask, pos)
+        y.backward(go.to(y.dtype)); x.grad = None
         for p in layer.parameters(): p.grad = None
     for _ in range(3): step()
     torch.cuda.synchronize()
