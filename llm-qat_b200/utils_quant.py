@@ -482,6 +482,7 @@ class QuantizeLinear(nn.Linear):
             and not self.act_layerwise
             and not self.weight_layerwise
             and input_.is_cuda
+            and input_.device == self.weight.device   # otherwise let F.linear raise its usual error
             and input_.dtype in _DTYPES
             and input_.dtype == self.weight.dtype
             and 1 <= input_.dim() <= 3
