@@ -123,3 +123,35 @@ def test_reduction_view_matches_reference_rules():
         _reduction_view(torch.zeros(1, 1, 1, 1, 1), False)      # utils_quant.py:69-70
     with pytest.raises(RuntimeError):                           # non-viewable 4-D raises like .view()
         _reduction_view(torch.zeros(2, 3, 4, 8).transpose(1, 2), False)
+
+
+def test_host_side_policy_knobs(monkeypatch):
+    """Host logic that needs no GPU: cache-mode parsing, the blob layout the forward and the
+    backward must agree on, the gates of the fused path, and the new ABI knobs."""
+    import llm_qat_b200
+    from llm_qat_b200 import QuantizeLinear
+    from llm_qat_b200 import utils_quant as uq
+
+    for env, want in (("0", 0), ("1", 1), ("2", 2), ("", 1), ("yes", 1)):
+        monkeypatch.setenv("QAT_B200_CACHE", env)
+        assert uq._cache_mode() == want
+    monkeypatch.delenv("QAT_B200_CACHE")
+    assert uq._cache_mode() == 1
+    assert not uq._in_backward_pass()                       # not inside autograd's engine here
+
+    off_e, off_m, total = uq._feed_layout(2048, 4096)       # codes | divisors | packed mask, 256 B aligned
+    assert off_e == 2048 * 4096 and off_m == off_e + 2048 * 4 and total == off_m + 2048 * 4096 // 8
+    off_e, off_m, total = uq._feed_layout(3, 40)
+    assert off_e == 256 and off_m == 512 and total == 512 + 15
+
+    lin = QuantizeLinear(32, 8, w_bits=4, a_bits=8)
+    assert not lin._can_fuse(torch.zeros(4, 32))            # CPU tensor: the unfused path raises "no CPU fallback"
+    assert not QuantizeLinear(32, 8, w_bits=16, a_bits=8)._can_fuse(torch.zeros(4, 32))
+    assert not uq._sym_amp(torch.zeros(4, 32, dtype=torch.bfloat16))   # CPU tensors never take the autocast variant
+
+    L = llm_qat_b200._lib.lib()
+    assert L.qat_set_gemm_cta_group(3) == 1001 and "cta_group" in llm_qat_b200._lib.last_error()
+    assert L.qat_set_gemm_cta_group(0) == 0 and L.qat_set_pdl(1) == 0
+    # the autocast variant exists for SymQuantizer only
+    assert L.qat_asym_fwd(16, 32, 0, 0, 0, 0, 0, -2.0, 2.0, 4, 4, 2, 4, 0, 0, 0) == 1001
+    assert L.qat_ste_bwd_devclip(16, 16, 32, 0, 0, 8, 0, 0) == 1001
