@@ -218,6 +218,53 @@ def test_fuzz_forward_backward_bit_exact_vs_oracle(seed):
         assert qo.count_mismatch(U.tensor_to_f32(xi.grad), gref) == 0, what
 
 
+# --------------------------------------------------------------- dependent chains, no host sync in between
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_dependent_kernel_chain_without_syncs(dtype):
+    """Every kernel is launched with programmatic dependent launch: its CTAs may be resident while
+    the previous kernel of the stream still runs.  A chain in which each launch consumes what the
+    previous one has just written (quantizer on quantizer output, K3 on fresh gradients, the GEMM
+    on fresh codes), enqueued back to back many times without a host synchronisation, must give the
+    oracle's bits — a misplaced griddepcontrol.wait would read half-written data."""
+    from llm_qat_b200 import _lib
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.utils_quant import fake_quant_forward, qlinear_i8, ste_backward
+
+    gen = torch.Generator().manual_seed(321)
+    x0 = (torch.randn(512, 4096, generator=gen) * 0.7).to(U.DTYPES[dtype])
+    g0 = torch.randn(512, 4096, generator=gen).to(U.DTYPES[dtype])
+    w = (torch.randn(256, 4096, generator=gen) * 0.05).to(U.DTYPES[dtype]).cuda()
+    xd, gd = x0.cuda(), g0.cuda()
+    plan = [(True, 8), (False, 8), (True, 4), (False, 4), (True, 6)]
+    finals = []
+    for rep in range(30):
+        t = xd
+        for sym, bits in plan:                       # each stage reads the previous stage's output
+            t = fake_quant_forward(t, bits, False, sym)[0]
+        gx = ste_backward(gd, t, CLIP)               # K3 on the chain's fresh output
+        gx = ste_backward(gx, xd, CLIP)              # and on K3's own fresh output
+        _, qx, _, ex, _ = fake_quant_forward(t, 8, False, True, want_y=False, codes_kind=CODES_I8, want_scales=True)
+        _, qw, _, ew, _ = fake_quant_forward(w, 4, False, True, want_y=False, codes_kind=CODES_I8, want_scales=True)
+        out = qlinear_i8(qx, qw, ex, ew, torch.float32)   # GEMM on codes written by the two launches before it
+        finals.append((t, gx, out))
+    torch.cuda.synchronize()
+    ref = U.tensor_to_f32(x0)
+    for sym, bits in plan:
+        ref = (qo.sym_forward if sym else qo.asym_forward)(ref, bits, False, dtype)["y"]
+    gref = qo.ste_backward(U.tensor_to_f32(g0), ref, -2.0, 2.0, dtype)["gx"]
+    gref = qo.ste_backward(gref, U.tensor_to_f32(x0), -2.0, 2.0, dtype)["gx"]
+    o = qo.sym_forward(ref, 8, False, dtype)
+    ow = qo.sym_forward(U.tensor_to_f32(w), 4, False, dtype)
+    dot = np.clip(o["codes"], -127, 127).astype(np.float64) @ np.clip(ow["codes"], -127, 127).astype(np.float64).T
+    oref = ((dot.astype(np.float32) * (np.float32(1) / o["e"].astype(np.float32))[:, None]) *
+            (np.float32(1) / ow["e"].astype(np.float32))[None, :]).astype(np.float32)
+    for t, gx, out in (finals[0], finals[-1], finals[13]):
+        assert qo.count_mismatch(U.tensor_to_f32(t), ref) == 0
+        assert qo.count_mismatch(U.tensor_to_f32(gx), gref) == 0
+        assert qo.count_mismatch(out.cpu().numpy(), oref) == 0
+    assert _lib.launch_count() > 0
+
+
 # --------------------------------------------------------------- config 5: LLaMA-13B shapes, 8 shards
 @pytest.mark.parametrize("shape,bits,what", [
     ((13824, 5120), 4, "gate/up_proj weight: sharded by output channel"),
