@@ -295,6 +295,38 @@ def time_shape_sweep(device, steps, pk):
             out[f"bf16_amp[{rows},{cols}] sym8 {mode}"] = {"fwd": {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
                                                                   "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}}
         del xs, ys, cs, ms
+    # the fused linear's backward helpers: rebuild bf16 operands from codes (3 B/elem) and the
+    # mask-driven STE (4.125 B/elem)
+    for rows, cols in ((11008, 4096), (8192, 4096), (2048, 4096)):
+        n = rows * cols
+        nbuf = max(2, -(-300_000_000 // (n * 4)))
+        cs = [torch.randint(-7, 8, (rows, cols), generator=g, dtype=torch.int8).to(device) for _ in range(2)]
+        cs += [cs[i % 2].clone() for i in range(nbuf - 2)]
+        es = (torch.rand(rows, generator=g) * 300 + 10).bfloat16().float().to(device)
+        outs = [torch.empty(rows, cols, dtype=torch.bfloat16, device=device) for _ in range(nbuf)]
+        gs = [torch.randn(rows, cols, generator=g).bfloat16().to(device)]
+        gs += [gs[0].clone() for _ in range(nbuf - 1)]
+        ms = [torch.randint(0, 256, (n // 8,), generator=g, dtype=torch.uint8).to(device)]
+        ms += [ms[0].clone() for _ in range(nbuf - 1)]
+        for mode, nbytes in (("dequant_codes", n * 3), ("ste_from_mask", n * 4 + n // 8)):
+            def once(i):
+                if mode == "dequant_codes":
+                    rc = L.qat_dequant_codes(cs[i].data_ptr(), es.data_ptr(), outs[i].data_ptr(), rows, cols, 1, st)
+                else:
+                    rc = L.qat_ste_bwd_from_mask(gs[i].data_ptr(), ms[i].data_ptr(), outs[i].data_ptr(), n, 1, st)
+                _lib.check(rc)
+            for i in range(nbuf):
+                once(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(steps):
+                once(k % nbuf)
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) / steps * 1e3
+            out[f"bf16[{rows},{cols}] {mode}"] = {"fwd": {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                                                         "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}}
+        del cs, outs, gs, ms
     return out
 
 

@@ -5,6 +5,8 @@
 // saturate.  QuantizeLinear's backward uses it for the dgrad/wgrad operands, so
 // the forward can save 1 B/elem of codes instead of the reference's two
 // dequantized tensors.  HBM-bound: 1 + sizeof(T) bytes per element.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qat {
@@ -12,63 +14,95 @@ namespace {
 
 constexpr int kThreads = 256;
 
-constexpr int kUnroll = 2;  // 16-byte code vectors per thread per tile, both loaded before use
+constexpr int kUnroll = 4;  // code groups per thread per tile, all loaded before use
+
+// Each thread turns one group of G = 16 / sizeof(out element) codes (8 for bf16, 4 for fp32) into
+// exactly ONE 16-byte store, so that every store instruction of a warp writes 512 contiguous
+// bytes — whole 32-byte sectors.  (A first version took 16 codes per thread and issued two
+// stores per thread, i.e. half sectors per instruction: 0.63 of the HBM peak at [11008, 4096];
+// the traffic is write-dominated, 1 B in : 2 B out.)
+template <int DT>
+struct Group {
+  static constexpr int kCodes = 16 / Num<DT>::kBytes;                 // 8 | 4
+  using load_t = typename std::conditional<DT == QAT_BF16, uint2, uint32_t>::type;
+};
 
 template <int DT>
-__device__ __forceinline__ void dequant_vec(const uint4& c, float e, void* out, int64_t j) {
+__device__ __forceinline__ uint4 dequant_group(typename Group<DT>::load_t c, float e) {
   const bool fast = recip_range_ok(e);
   const float r = __frcp_rn(e);
   // bf16 output and a bf16-valued divisor (what K1 emits for bf16 tensors): one multiply is
   // exact — see SymScale::mulq in common.cuh
   const bool mulq = DT == QAT_BF16 && fast && Num<QAT_BF16>::fl(e) == e;
-  const uint32_t w[4] = {c.x, c.y, c.z, c.w};
-  float y[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const float q = (float)(int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-    y[k] = mulq ? __fmul_rn(q, r) : fast ? div_code_by_recip(q, e, r) : __fdiv_rn(q, e);
-  }
-  if (DT == QAT_BF16) {
-    uint4* o = reinterpret_cast<uint4*>(out) + 2 * j;
-    stg_stream(o, make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                             pack_bf16x2(y[6], y[7])));
-    stg_stream(o + 1, make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]),
-                                 pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15])));
+  constexpr int G = Group<DT>::kCodes;
+  uint32_t w[2];
+  if constexpr (DT == QAT_BF16) {
+    w[0] = c.x;
+    w[1] = c.y;
   } else {
-    uint4* o = reinterpret_cast<uint4*>(out) + 4 * j;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      stg_stream(o + k, make_uint4(__float_as_uint(y[4 * k]), __float_as_uint(y[4 * k + 1]),
-                                   __float_as_uint(y[4 * k + 2]), __float_as_uint(y[4 * k + 3])));
+    w[0] = c;
+    w[1] = 0u;
   }
+  float y[G];
+#pragma unroll
+  for (int k = 0; k < G; ++k) y[k] = (float)(int)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+  // one (nearly always warp-uniform) branch per group, not a select per element: the exact
+  // division's slow path is a long instruction sequence that must stay out of the common stream
+  if (mulq) {
+#pragma unroll
+    for (int k = 0; k < G; ++k) y[k] = __fmul_rn(y[k], r);
+  } else if (fast) {
+#pragma unroll
+    for (int k = 0; k < G; ++k) y[k] = div_code_by_recip(y[k], e, r);
+  } else {
+#pragma unroll
+    for (int k = 0; k < G; ++k) y[k] = __fdiv_rn(y[k], e);
+  }
+  if constexpr (DT == QAT_BF16)
+    return make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4 % G], y[5 % G]),
+                      pack_bf16x2(y[6 % G], y[7 % G]));
+  else
+    return make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
 }
 
-// one 16-byte vector of codes (16 elements of one row) per thread and unroll
-// step; IDX32: the vector index fits 32 bits, so the row lookup is a 32-bit
-// division instead of a 64-bit one (~60 instructions per vector).
+// IDX32: the group index fits 32 bits, so the row lookup is a multiply-high by a host-computed
+// magic number (exact for every j < 2^32: Granlund-Montgomery round-up method with a 33-bit
+// multiplier) instead of a 64-bit division (~60 instructions per group).
+struct Magic {
+  uint32_t mul;   // low 32 bits of the 33-bit multiplier
+  uint32_t shift; // post-shift
+  uint32_t pow2;  // divisor is a power of two: row = j >> shift
+};
+__device__ __forceinline__ uint32_t magic_div(uint32_t j, const Magic& m) {
+  if (m.pow2) return j >> m.shift;
+  const uint32_t t = __umulhi(j, m.mul);
+  return (t + ((j - t) >> 1)) >> m.shift;   // (j * (2^32 + mul)) >> (33 + shift) without overflow
+}
+
 template <int DT, bool IDX32>
 __global__ void __launch_bounds__(kThreads) dequant_codes_kernel(const int8_t* __restrict__ codes,
                                                                  const float* __restrict__ row_e,
-                                                                 void* __restrict__ out, int64_t nvec,
-                                                                 int vec_per_row) {
+                                                                 void* __restrict__ out, int64_t ngroups,
+                                                                 int groups_per_row, const Magic magic) {
+  using L = typename Group<DT>::load_t;
   constexpr int64_t kTile = (int64_t)kThreads * kUnroll;
   pdl_wait();
   pdl_launch_dependents();
-  for (int64_t base = (int64_t)blockIdx.x * kTile; base < nvec; base += (int64_t)gridDim.x * kTile) {
-    uint4 c[kUnroll];
+  for (int64_t base = (int64_t)blockIdx.x * kTile; base < ngroups; base += (int64_t)gridDim.x * kTile) {
+    L c[kUnroll];
     float e[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = base + (int64_t)u * kThreads + threadIdx.x;
-      if (j < nvec) {
-        c[u] = ldg_stream(reinterpret_cast<const uint4*>(codes) + j);
-        e[u] = row_e[IDX32 ? (int64_t)((uint32_t)j / (uint32_t)vec_per_row) : j / vec_per_row];
+      if (j < ngroups) {
+        c[u] = __ldg(reinterpret_cast<const L*>(codes) + j);
+        e[u] = row_e[IDX32 ? (int64_t)magic_div((uint32_t)j, magic) : j / groups_per_row];
       }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int64_t j = base + (int64_t)u * kThreads + threadIdx.x;
-      if (j < nvec) dequant_vec<DT>(c[u], e[u], out, j);
+      if (j < ngroups) stg_stream(reinterpret_cast<uint4*>(out) + j, dequant_group<DT>(c[u], e[u]));
     }
   }
 }
@@ -85,21 +119,37 @@ extern "C" int qat_dequant_codes(const int8_t* codes, const float* row_e, void* 
   QAT_CHECK_ARG(codes && row_e && out, "NULL operand");
   QAT_CHECK_ARG(cols % 16 == 0, "cols must be a multiple of 16 (got %lld)", (long long)cols);
   QAT_CHECK_ARG(((uintptr_t)codes & 15) == 0 && ((uintptr_t)out & 15) == 0, "pointers must be 16-byte aligned");
-  const int64_t nvec = rows * cols / 16;
-  QAT_CHECK_ARG(cols / 16 < (1ll << 31), "row too long");
-  int64_t grid = (nvec + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+  const int per = dtype == QAT_BF16 ? 8 : 4;    // codes per thread-iteration == one 16-byte store
+  const int64_t ngroups = rows * cols / per;
+  QAT_CHECK_ARG(cols / per < (1ll << 31), "row too long");
+  int64_t grid = (ngroups + kThreads * kUnroll - 1) / (kThreads * kUnroll);
   const int64_t cap = (int64_t)num_sms() * 8;   // 8 resident CTAs per SM
   if (grid > cap) grid = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool idx32 = nvec < (1ll << 32);
-  const int vpr = (int)(cols / 16);
+  const bool idx32 = ngroups < (1ll << 32);
+  const int gpr = (int)(cols / per);
+  Magic magic{};
+  {
+    const uint32_t d = (uint32_t)gpr;
+    if ((d & (d - 1)) == 0) {
+      magic.pow2 = 1;
+      while ((1u << magic.shift) < d) ++magic.shift;
+    } else {
+      uint32_t l = 0;
+      while ((1ull << l) < d) ++l;                                    // l = ceil(log2 d), d not a power of two
+      const unsigned __int128 one = 1;
+      const uint64_t m = (uint64_t)(((one << (32 + l)) / d) + 1);    // 2^32 <= m < 2^33
+      magic.mul = (uint32_t)(m - (1ull << 32));
+      magic.shift = l - 1;
+    }
+  }
   const dim3 g((unsigned)grid), b(kThreads);
   if (dtype == QAT_BF16) {
-    if (idx32) (void)launch_pdl(dequant_codes_kernel<QAT_BF16, true>, g, b, 0, st, codes, row_e, out, nvec, vpr);
-    else (void)launch_pdl(dequant_codes_kernel<QAT_BF16, false>, g, b, 0, st, codes, row_e, out, nvec, vpr);
+    if (idx32) (void)launch_pdl(dequant_codes_kernel<QAT_BF16, true>, g, b, 0, st, codes, row_e, out, ngroups, gpr, magic);
+    else (void)launch_pdl(dequant_codes_kernel<QAT_BF16, false>, g, b, 0, st, codes, row_e, out, ngroups, gpr, magic);
   } else {
-    if (idx32) (void)launch_pdl(dequant_codes_kernel<QAT_F32, true>, g, b, 0, st, codes, row_e, out, nvec, vpr);
-    else (void)launch_pdl(dequant_codes_kernel<QAT_F32, false>, g, b, 0, st, codes, row_e, out, nvec, vpr);
+    if (idx32) (void)launch_pdl(dequant_codes_kernel<QAT_F32, true>, g, b, 0, st, codes, row_e, out, ngroups, gpr, magic);
+    else (void)launch_pdl(dequant_codes_kernel<QAT_F32, false>, g, b, 0, st, codes, row_e, out, ngroups, gpr, magic);
   }
   QAT_CHECK_LAUNCH("dequant_codes_kernel");
   return QAT_OK;
