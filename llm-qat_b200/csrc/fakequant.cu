@@ -476,27 +476,53 @@ __global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
     constexpr int OV = Num<DT>::kOutBytes / Num<DT>::kBytes;  // output vectors per input vector
     uint4* yrow = reinterpret_cast<uint4*>(p.y) + row * p.nvec * OV;
     asm volatile("" : "+l"(yrow));
-    if (sc.fast) {  // row-uniform => warp-uniform: a warp never spans two rows
+    if constexpr (OV == 1) {
+      if (sc.fast) {  // row-uniform => warp-uniform: a warp never spans two rows
 #pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const uint32_t j = t + (uint32_t)i * group;
-        uint4 o[OV];
-        quant_vec_y<DT, SYM, true>(sc, v[i], o);
-        if (j < nvec) {
+        for (int i = 0; i < ITERS; ++i) {
+          const uint32_t j = t + (uint32_t)i * group;
+          uint4 o[1];
+          quant_vec_y<DT, SYM, true>(sc, v[i], o);
+          if (j < nvec) stg_stream(yrow + j, o[0]);
+        }
+      } else {
 #pragma unroll
-          for (int k = 0; k < OV; ++k) stg_stream(yrow + j * OV + k, o[k]);
+        for (int i = 0; i < ITERS; ++i) {
+          const uint32_t j = t + (uint32_t)i * group;
+          uint4 o[1];
+          quant_vec_y<DT, SYM, false>(sc, v[i], o);
+          if (j < nvec) stg_stream(yrow + j, o[0]);
         }
       }
     } else {
+      // y elements are twice as wide as x elements: a lane holds 32 consecutive output bytes.
+      // Storing them as two 16-byte pieces per lane would make every store instruction write
+      // HALF of each 32-byte sector (measured: the L2 then handles twice the write transactions
+      // and the kernel ran at 0.71 of the HBM peak).  The warp's 64 pieces go through a
+      // bank-conflict-free swizzled shared-memory exchange instead, so that each store
+      // instruction writes 512 contiguous bytes.
+      __shared__ uint4 stage[2048];                        // 64 pieces per warp, up to 32 warps
+      uint4* ws = stage + (threadIdx.x >> 5) * 64;
+      const uint32_t lane = threadIdx.x & 31u;
+      const uint32_t w0 = 2u * lane, w1 = 2u * lane + 1u;  // pieces this lane produces
+      const uint32_t r0 = lane, r1 = 32u + lane;           // pieces this lane stores
+      auto sw = [](uint32_t c) { return c ^ ((c >> 3) & 1u); };
 #pragma unroll
       for (int i = 0; i < ITERS; ++i) {
         const uint32_t j = t + (uint32_t)i * group;
+        const uint32_t jw = j - lane;                      // the warp's first vector of this step
         uint4 o[OV];
-        quant_vec_y<DT, SYM, false>(sc, v[i], o);
-        if (j < nvec) {
-#pragma unroll
-          for (int k = 0; k < OV; ++k) stg_stream(yrow + j * OV + k, o[k]);
-        }
+        if (sc.fast)
+          quant_vec_y<DT, SYM, true>(sc, v[i], o);
+        else
+          quant_vec_y<DT, SYM, false>(sc, v[i], o);
+        ws[sw(w0)] = o[0];
+        ws[sw(w1)] = o[1];
+        __syncwarp();
+        const uint4 a = ws[sw(r0)], b = ws[sw(r1)];
+        __syncwarp();
+        if (jw + (r0 >> 1) < nvec) stg_stream(yrow + (size_t)jw * OV + r0, a);
+        if (jw + (r1 >> 1) < nvec) stg_stream(yrow + (size_t)jw * OV + r1, b);
       }
     }
   } else if constexpr (OUT == OUT_FEED) {
