@@ -409,7 +409,8 @@ __device__ __forceinline__ void quant_vec_feed(const FwdParams& p, const Scale& 
   }
   uint32_t cw[N / 4];
 #pragma unroll
-  for (int i = 0; i < N / 4; ++i) cw[i] = pack_codes4<SYM>(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
+  for (int i = 0; i < N / 4; ++i)
+    cw[i] = pack_codes4<SYM, DT == QAT_BF16>(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
   if (valid) {
     if (N == 4)
       *reinterpret_cast<uint32_t*>(codes_row + (size_t)j * N) = cw[0];
@@ -418,10 +419,15 @@ __device__ __forceinline__ void quant_vec_feed(const FwdParams& p, const Scale& 
   }
   if (mask_row != nullptr) {
     uint32_t pass = 0;
+    if (p.lo == -p.hi) {   // the model's clip is always [-c, c]: one compare on |x| (NaN passes, inf is masked)
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const float xf = vec_get<DT>(v, i);
-      pass |= ((xf >= p.hi || xf <= p.lo) ? 0u : 1u) << i;  // utils_quant.py:85-86
+      for (int i = 0; i < N; ++i) pass |= ((fabsf(vec_get<DT>(v, i)) >= p.hi) ? 0u : 1u) << i;
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float xf = vec_get<DT>(v, i);
+        pass |= ((xf >= p.hi || xf <= p.lo) ? 0u : 1u) << i;  // utils_quant.py:85-86
+      }
     }
     if (N == 8) {
       if (valid) mask_row[j] = (uint8_t)pass;
