@@ -38,6 +38,7 @@ struct FwdParams {
   // long-row path
   uint32_t* ws;
   int64_t chunk;  // vectors per CTA
+  int poison_inf;  // Sym GEMM feed: e = NaN for rows whose abs-max is +inf (see sym_fwd_feed)
 };
 
 // ---- reductions --------------------------------------------------------------
@@ -475,7 +476,11 @@ __global__ void __launch_bounds__(1024) rowquant_vec_kernel(const FwdParams p) {
   const typename SO::type sc = warp_derive_scale<DT, SYM>(st, p.qmax);
   if (t == 0 && row_ok) {
     if (p.st0 != nullptr) p.st0[row] = SO::st0(sc);
-    if (p.st1 != nullptr) p.st1[row] = SO::st1(sc);
+    if (p.st1 != nullptr) {
+      float st1 = SO::st1(sc);
+      if (SYM && OUT == OUT_FEED && p.poison_inf && st.amax_bits == 0x7f800000u) st1 = __int_as_float(0x7fc00000);
+      p.st1[row] = st1;
+    }
   }
 
   if constexpr (OUT == OUT_Y) {
@@ -853,7 +858,7 @@ float round_to_dtype(float v, int dtype) {
 template <bool SYM>
 int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, float* st1,
               uint8_t* mask, float lo, float hi, int64_t rows, int64_t cols, int dtype, int bits,
-              void* workspace, size_t workspace_bytes, void* stream) {
+              void* workspace, size_t workspace_bytes, void* stream, int poison_inf = 0) {
   QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16 || (SYM && dtype == QAT_BF16_AMP),
                 "dtype must be QAT_F32, QAT_BF16 or (Sym only) QAT_BF16_AMP (got %d)", dtype);
   QAT_CHECK_ARG(rows >= 0 && cols >= 0, "negative shape [%lld, %lld]", (long long)rows, (long long)cols);
@@ -906,6 +911,7 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
   while ((1 << p.log2_group) < pl.group) ++p.log2_group;
   p.ws = reinterpret_cast<uint32_t*>(workspace);
   p.chunk = pl.chunk;
+  p.poison_inf = poison_inf;
   if (!pl.fused) {
     const size_t need = (size_t)rows * 16;
     if (workspace == nullptr || workspace_bytes < need) {
@@ -923,6 +929,12 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
 }
 
 }  // namespace
+
+int sym_fwd_feed(const void* x, void* codes, float* row_e, uint8_t* mask, float clip_lo, float clip_hi,
+                 int64_t rows, int64_t cols, int dtype, int bits, void* stream) {
+  return fwd_entry<true>(x, nullptr, codes, QAT_CODES_I8, nullptr, row_e, mask, clip_lo, clip_hi, rows, cols,
+                         dtype, bits, nullptr, 0, stream, /*poison_inf=*/1);
+}
 }  // namespace qat
 
 extern "C" {

@@ -593,13 +593,11 @@ extern "C" int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, in
   QAT_CHECK_ARG(qx && ex && qw && ew, "code / scale buffers must be provided");
   QAT_CHECK_ARG(a_bits >= 2 && a_bits <= 8 && w_bits >= 2 && w_bits <= 8, "int8 grid needs 2 <= bits <= 8");
   if (!reuse_x) {
-    int rc = qat_sym_fwd(x, nullptr, qx, QAT_CODES_I8, nullptr, ex, mx, clip_lo, clip_hi, T, K, dtype, a_bits,
-                         nullptr, 0, stream);
+    int rc = sym_fwd_feed(x, qx, ex, mx, clip_lo, clip_hi, T, K, dtype, a_bits, stream);
     if (rc != QAT_OK) return rc;
   }
   if (!reuse_w) {
-    int rc = qat_sym_fwd(w, nullptr, qw, QAT_CODES_I8, nullptr, ew, mw, clip_lo, clip_hi, N, K, dtype, w_bits,
-                         nullptr, 0, stream);
+    int rc = sym_fwd_feed(w, qw, ew, mw, clip_lo, clip_hi, N, K, dtype, w_bits, stream);
     if (rc != QAT_OK) return rc;
   }
   // under autocast the reference's F.linear runs, and returns, bf16

@@ -533,6 +533,34 @@ def test_sym_quantizer_under_autocast_is_the_fp32_scale_chain(bits):
             assert qo.count_mismatch(e.cpu().numpy(), o["e"]) == 0
 
 
+def test_fused_linear_propagates_nonfinite_rows_like_the_reference():
+    """An overflowed activation (or weight) row must not vanish: the reference's fake-quantized row
+    holds NaN (inf * 0, or NaN itself) and so does its output row (column); the integer codes of
+    NaN are 0, so the fused path carries the information in the row divisor instead."""
+    from llm_qat_b200 import QuantizeLinear
+    from oracle import ref_module as R
+
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(64, 256, generator=gen).bfloat16()
+    w = (torch.randn(128, 256, generator=gen) * 0.05).bfloat16()
+    x[3, 17] = float("inf")
+    x[9, 200] = float("nan")
+    x[20, 5] = -float("inf")
+    w[40, 3] = float("inf")
+    w[77, 100] = float("nan")
+    outs = []
+    for mod in (R, None):
+        lin = (mod.QuantizeLinear if mod else QuantizeLinear)(256, 128, w_bits=4, a_bits=8).bfloat16().cuda()
+        with torch.no_grad():
+            lin.weight.copy_(w.cuda())
+            outs.append(lin(x.cuda()).float().cpu())
+    ref, got = outs
+    assert torch.equal(torch.isnan(ref), torch.isnan(got))
+    assert torch.isnan(got[3]).all() and torch.isnan(got[:, 40]).all() and not torch.isnan(got[0, 0])
+    ok = ~torch.isnan(ref)
+    assert ((ref[ok] - got[ok]).norm() / ref[ok].norm()).item() <= 1e-2
+
+
 def test_quantize_linear_under_autocast_matches_reference_semantics():
     """HF's Trainer wraps the step in torch.autocast(bf16) (kd_trainer.py:106).  With fp32 modules the
     reference fake-quantizes in fp32 and its F.linear then runs — and returns — bf16; with bf16 modules
