@@ -561,13 +561,17 @@ def test_fused_linear_propagates_nonfinite_rows_like_the_reference():
     assert ((ref[ok] - got[ok]).norm() / ref[ok].norm()).item() <= 1e-2
 
 
-def test_quantize_linear_under_autocast_matches_reference_semantics():
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_quantize_linear_under_autocast_matches_reference_semantics(fused, monkeypatch):
     """HF's Trainer wraps the step in torch.autocast(bf16) (kd_trainer.py:106).  With fp32 modules the
     reference fake-quantizes in fp32 and its F.linear then runs — and returns — bf16; with bf16 modules
-    autocast is a no-op.  The product must give the same dtypes and values in both cases."""
+    its SymQuantizer switches to the fp32 scale chain and returns float32, which F.linear casts back.
+    The product must give the same dtypes and values in both cases: bit-identical on the unfused path
+    (same op chain, same library GEMM), within the GEMM tolerance on the integer-grid path."""
     from llm_qat_b200 import QuantizeLinear
     from oracle import ref_module as R
 
+    monkeypatch.setenv("QAT_B200_FUSED_LINEAR", fused)
     gen = torch.Generator().manual_seed(3)
     x32 = torch.randn(6, 40, 256, generator=gen).cuda()
     w32 = (torch.randn(128, 256, generator=gen) * 0.05).cuda()
@@ -588,8 +592,8 @@ def test_quantize_linear_under_autocast_matches_reference_semantics():
         for a, c in ((o_ref, o), (dx_ref, dx), (dw_ref, dw)):
             rel = ((a.double() - c.double()).norm() / a.double().norm()).item()
             assert rel <= 1e-2, (dtype, rel)
-        if dtype == torch.float32:      # unfused under autocast: the very same op chain as the reference
-            assert torch.equal(o_ref, o)
+        if fused == "0" or dtype == torch.float32:   # the very same op chain as the reference
+            assert torch.equal(o_ref, o) and torch.equal(dx_ref, dx) and torch.equal(dw_ref, dw), dtype
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
