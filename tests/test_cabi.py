@@ -155,3 +155,37 @@ def test_host_side_policy_knobs(monkeypatch):
     # the autocast variant exists for SymQuantizer only
     assert L.qat_asym_fwd(16, 32, 0, 0, 0, 0, 0, -2.0, 2.0, 4, 4, 2, 4, 0, 0, 0) == 1001
     assert L.qat_ste_bwd_devclip(16, 16, 32, 0, 0, 8, 0, 0) == 1001
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/qat_b200.h must be consumable by a C compiler (no C++ or torch types across the
+    ABI), and a C program must link against the shared library and reach the no-GPU entry points."""
+    import shutil
+    import subprocess
+
+    import llm_qat_b200
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "qat_b200.h"
+int main(void) {
+  if (qat_version() != QAT_B200_VERSION) return 1;
+  /* bad dtype: rejected before any pointer is touched, with a message */
+  if (qat_sym_fwd((const void*)16, (void*)32, 0, QAT_CODES_NONE, 0, 0, 0, -2.0f, 2.0f, 4, 4, 9, 4, 0, 0, 0) != QAT_ERR_BAD_ARG) return 2;
+  if (qat_last_error()[0] == 0) return 3;
+  if (qat_fwd_workspace_bytes(8192, 4096, QAT_BF16) != 0) return 4;
+  if (qat_host_scratch_bytes(8, 16, QAT_BF16, 1) != 4 * 256) return 5;
+  printf("abi ok %d\n", qat_version());
+  return 0;
+}
+''')
+    lib_dir = os.path.dirname(llm_qat_b200._lib.LIB_PATH)
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                    "-L", lib_dir, "-l:libqat_b200.so", "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "abi ok 100" in r.stdout, (r.returncode, r.stdout, r.stderr)
