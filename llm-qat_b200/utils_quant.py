@@ -136,7 +136,16 @@ def fake_quant_forward(input: torch.Tensor, num_bits: int, layerwise: bool, symm
         dt = QAT_BF16_AMP
     rows, cols = _reduction_view(input, layerwise)
     if input.numel() == 0:
-        raise RuntimeError("fake-quant of an empty tensor (the reference's max() raises too)")
+        # what the reference's torch.max does: an empty reduction set raises (IndexError for
+        # max(dim=-1) over zero columns, RuntimeError for the layerwise max() of nothing), but zero
+        # ROWS of a non-empty width are simply zero reductions and the result is an empty tensor
+        if layerwise:
+            raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0. "
+                               "Specify the reduction dim with the 'dim' argument.")
+        if cols == 0:
+            raise IndexError("max(): Expected reduction dim to have non-zero size.")
+        empty = torch.empty(input.shape, dtype=torch.float32 if amp else input.dtype, device=input.device)
+        return (empty if want_y else None), None, None, None, None
     x = input.detach()
     if not x.is_contiguous():
         x = x.contiguous()

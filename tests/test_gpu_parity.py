@@ -305,6 +305,32 @@ def test_config5_shards_reassemble_bit_exact(shape, bits, what):
     assert qo.count_mismatch(U.tensor_to_f32(y[:64]), qo.sym_forward(U.tensor_to_f32(flat[:64]), bits, False, "bf16")["y"]) == 0
 
 
+def test_empty_inputs_behave_like_the_reference():
+    """Zero rows of a non-empty width: an empty result (and gradient); an empty reduction set
+    (zero columns, or layerwise over nothing) raises what torch.max raises in the reference;
+    QuantizeLinear on zero tokens returns [0, out]."""
+    from llm_qat_b200 import AsymQuantizer, QuantizeLinear, SymQuantizer
+
+    for Q in (SymQuantizer, AsymQuantizer):
+        x = torch.zeros(0, 8, device="cuda", requires_grad=True)
+        y = Q.apply(x, CLIP, 4, False)
+        assert y.shape == (0, 8) and y.dtype == x.dtype
+        y.sum().backward()
+        assert x.grad.shape == (0, 8)
+        assert Q.apply(torch.zeros(2, 0, 8, device="cuda"), CLIP, 4, False).shape == (2, 0, 8)
+        with pytest.raises(IndexError):
+            Q.apply(torch.zeros(4, 0, device="cuda"), CLIP, 4, False)
+        with pytest.raises(RuntimeError):
+            Q.apply(torch.zeros(0, 8, device="cuda"), CLIP, 4, True)
+    # a 0-dim tensor is one row of one element
+    for val in (1.7, -0.3, 0.0):
+        y = SymQuantizer.apply(torch.tensor(val, device="cuda"), CLIP, 4, False)
+        assert y.shape == () and qo.count_mismatch(U.tensor_to_f32(y).reshape(1), qo.sym_forward(np.float32([val]), 4)["y"]) == 0
+    lin = QuantizeLinear(16, 4, w_bits=4, a_bits=8).bfloat16().cuda()
+    assert lin(torch.zeros(0, 16, device="cuda", dtype=torch.bfloat16)).shape == (0, 4)
+    assert lin(torch.zeros(2, 0, 16, device="cuda", dtype=torch.bfloat16)).shape == (2, 0, 4)
+
+
 # --------------------------------------------------------------- full BASELINE sizes: properties
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_config1_full_size_properties(dtype):
