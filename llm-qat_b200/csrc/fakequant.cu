@@ -862,8 +862,9 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
   QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16 || (SYM && dtype == QAT_BF16_AMP),
                 "dtype must be QAT_F32, QAT_BF16 or (Sym only) QAT_BF16_AMP (got %d)", dtype);
   QAT_CHECK_ARG(rows >= 0 && cols >= 0, "negative shape [%lld, %lld]", (long long)rows, (long long)cols);
-  QAT_CHECK_ARG(SYM ? (bits >= 2 && bits <= 16) : (bits >= 1 && bits <= 15),
-                "unsupported num_bits %d", bits);
+  QAT_CHECK_ARG(SYM ? (bits >= 2 && bits <= 31) : (bits >= 1 && bits <= 31), "unsupported num_bits %d", bits);
+  QAT_CHECK_ARG(!(codes != nullptr && codes_kind == QAT_CODES_I16 && bits > (SYM ? 16 : 15)),
+                "int16 codes need num_bits <= %d (got %d)", SYM ? 16 : 15, bits);
   if (rows == 0 || cols == 0) return QAT_OK;
   QAT_CHECK_ARG(x != nullptr, "x is NULL");
   QAT_CHECK_ARG(y != nullptr || codes != nullptr || st0 != nullptr || st1 != nullptr || mask != nullptr,
@@ -905,7 +906,8 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
   p.rows = rows;
   p.cols = cols;
   p.nvec = pl.nvec;
-  p.qmax = SYM ? (float)((1 << (bits - 1)) - 1) : (float)((1 << bits) - 1);
+  // the reference's Python int, converted to the fp32 op scalar (round to nearest)
+  p.qmax = SYM ? (float)((1ll << (bits - 1)) - 1) : (float)((1ll << bits) - 1);
   p.group = pl.group;
   p.log2_group = 0;
   while ((1 << p.log2_group) < pl.group) ++p.log2_group;

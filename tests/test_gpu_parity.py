@@ -218,6 +218,21 @@ def test_fuzz_forward_backward_bit_exact_vs_oracle(seed):
         assert qo.count_mismatch(U.tensor_to_f32(xi.grad), gref) == 0, what
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_wide_bit_widths_take_the_exact_division(dtype):
+    """num_bits up to 31 (the reference accepts any): codes beyond 15/16 bits leave the proven range
+    of the reciprocal-based quotient, so those rows divide exactly — still bit for bit."""
+    gen = torch.Generator().manual_seed(17)
+    x = (torch.randn(24, 1000, generator=gen) * 1.3).to(U.DTYPES[dtype])
+    x[0] = 0.0
+    x[1, :5] = torch.tensor([2.0, -2.0, -0.0, 1e-20, -3e4]).to(x.dtype)
+    xn = U.tensor_to_f32(x)
+    for q, fn, widths in (("sym", qo.sym_forward, (16, 17, 20, 24, 25, 31)), ("asym", qo.asym_forward, (15, 16, 20, 24, 31))):
+        for bits in widths:
+            y = _q(q).apply(x.cuda(), CLIP, bits, False)
+            assert qo.count_mismatch(U.tensor_to_f32(y), fn(xn, bits, False, dtype)["y"]) == 0, (q, bits, dtype)
+
+
 # --------------------------------------------------------------- dependent chains, no host sync in between
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_dependent_kernel_chain_without_syncs(dtype):
