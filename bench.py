@@ -366,9 +366,9 @@ def time_qlinear(device, x, w, steps, pk):
     # plain bf16 peak is kept beside it, and the ncu tensor-pipe-active share from profiles/.
     peak_i8 = 2.0 * pk["bf16_tflops"]
     res["roofline"] = {"bound": "tensor", "achieved": res["gemm"]["TOPs"], "peak": round(peak_i8, 1),
-                       "unit": "TOP/s (int8 MAC x2)", "frac": round(res["gemm"]["TOPs"] / peak_i8, 4),
+                       "unit": "TOP/s", "frac": round(res["gemm"]["TOPs"] / peak_i8, 4),
                        "frac_of_bf16_peak": round(res["gemm"]["TOPs"] / pk["bf16_tflops"], 4),
-                       "peak_source": "2 x bf16_tflops of " + pk["source"],
+                       "peak_source": "2 x bf16_tflops of " + pk["source"] + " (int8 MMA: twice the bf16 MAC rate)",
                        "tensor_pipe_active_ncu": NCU_GEMM.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                        "traffic": NCU_GEMM.get("dram_bytes_per_launch"),
                        "kernel": "qlinear_i8_kernel<bf16, cta_group 2> 8192x11008x4096"}
