@@ -226,3 +226,38 @@ def test_fused_linear_is_the_grid_statement_bit_for_bit(dtype):
         for a, c in zip(res[0][1:], res[1][1:]):
             rel = ((a.double() - c.double()).norm() / a.double().norm().clamp_min(1e-30)).item()
             assert rel <= (1e-2 if dtype == torch.bfloat16 else 1e-5), what
+
+
+@needs_reference
+def test_reference_model_file_builds_on_the_product_module():
+    """The drop-in claim at the import boundary: with llm_qat_b200 installed under the name
+    `models.utils_quant`, the UNMODIFIED reference model file (modeling_llama_quant.py:51 imports
+    QuantizeLinear and SymQuantizer from it) constructs its LLaMA with the product's classes, and
+    its state dict keeps the reference's keys.  (No forward here: the product has no CPU path.)"""
+    import importlib
+    import subprocess
+
+    code = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, %r)
+import llm_qat_b200
+import models                                   # the reference package
+llm_qat_b200.install()                          # models.utils_quant -> the product
+from models.configuration_llama import LlamaConfig
+from models import modeling_llama_quant as M
+assert M.QuantizeLinear is llm_qat_b200.QuantizeLinear and M.SymQuantizer is llm_qat_b200.SymQuantizer
+cfg = LlamaConfig(hidden_size=64, intermediate_size=176, num_attention_heads=4, num_hidden_layers=2, vocab_size=128,
+                  max_position_embeddings=64, w_bits=4, a_bits=8, kv_bits=4)
+cfg.kv_bits = 4
+model = M.LlamaForCausalLM(cfg)
+lin = [m for m in model.modules() if isinstance(m, llm_qat_b200.QuantizeLinear)]
+assert len(lin) == 2 * 7, len(lin)
+att = model.model.layers[0].self_attn
+assert att.act_quantizer_k is llm_qat_b200.SymQuantizer and att.kv_bits == 4
+keys = sorted(model.state_dict().keys())
+assert all(not k.endswith("_qat_wfeed") for k in keys) and "model.layers.0.mlp.up_proj.weight" in keys
+print("ok", len(keys))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr[-3000:]
