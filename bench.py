@@ -543,8 +543,8 @@ def run_b200(args):
             del step, x, w, gx, gw
             torch.cuda.empty_cache()
             torch.cuda.reset_peak_memory_stats()
-            r = QB.time_qat_step(llm_qat_b200.utils_quant, cfg7, seq=2048, bsz=1, warmup=2,
-                                 steps=max(3, min(K, 5)), device=device, rank=rank, world=world,
+            r = QB.time_qat_step(llm_qat_b200.utils_quant, cfg7, seq=2048, bsz=1, warmup=3,
+                                 steps=max(3, min(K, 10)), device=device, rank=rank, world=world,
                                  autocast=True)   # the recipe: HF's Trainer runs the step in autocast(bf16)
             ms = r["ms_per_step"]
             if dist is not None:

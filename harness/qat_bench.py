@@ -56,7 +56,7 @@ def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, dev
             "autocast": autocast}
 
 
-def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=2, steps=5, device="cuda", rank=0, world=1,
+def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, device="cuda", rank=0, world=1,
                   lr=2e-5, autocast=False):
     """Config 4/5: student (quantized) + frozen FP teacher of identical init, KD loss,
     gradient checkpointing, AdamW; DDP (NCCL all-reduce of the gradients) when world > 1.
