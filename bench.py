@@ -327,6 +327,32 @@ def time_shape_sweep(device, steps, pk):
             out[f"bf16[{rows},{cols}] {mode}"] = {"fwd": {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
                                                          "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}}
         del cs, outs, gs, ms
+    # QuantizeLinear's W1 / W2 weight path (utils_quant.py:202-242): mean|w| per row, then apply, in one
+    # pass with the row in registers: 2e B/elem
+    for dt_name, dt, tdt, esz in (("bf16", 1, torch.bfloat16, 2), ("fp32", 0, torch.float32, 4)):
+        rows, cols = 11008, 4096
+        n = rows * cols
+        ws_ = [(torch.randn(rows, cols, generator=g) * 0.02).to(tdt).to(device) for _ in range(2)]
+        ws_ += [ws_[0].clone()]
+        outs = [torch.empty_like(t) for t in ws_]
+        wsp = torch.empty(int(L.qat_lowbit_workspace_bytes(rows, 0)), dtype=torch.uint8, device=device)
+        for bits in (1, 2):
+            def once(i):
+                _lib.check(L.qat_lowbit_weight_fwd(ws_[i].data_ptr(), outs[i].data_ptr(), rows, cols, dt, bits, 0,
+                                                   wsp.data_ptr(), wsp.numel(), st))
+            for i in range(3):
+                once(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(steps):
+                once(k % 3)
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) / steps * 1e3
+            nbytes = n * esz * 2
+            out[f"{dt_name}[{rows},{cols}] lowbit_w{bits}"] = {"fwd": {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                                                                      "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}}
+        del ws_, outs
     return out
 
 

@@ -79,8 +79,30 @@ static int check_addsub(void) {
   return bad != 0;
 }
 
+/* Third claim (argv[1] == "anyratio", ~8.4e8 quotients): the same single-multiply quotient for
+ * ANY finite bf16 numerator, not only d <= a — the W1/W2 weight path divides each weight by its
+ * row's mean |w| (utils_quant.py:211,229), and a weight can be far above or below the mean. */
+static int check_anyratio(void) {
+  long long bad = 0, total = 0;
+#pragma omp parallel for reduction(+ : bad, total) schedule(dynamic, 64)
+  for (int ab = (27 << 7); ab < (228 << 7); ++ab) {
+    const float a = bf16_to_f((uint16_t)ab);
+    const float ra = 1.0f / a;
+    for (int db = 0; db < (255 << 7); ++db) {            /* every finite non-negative bf16 numerator */
+      const float d = bf16_to_f((uint16_t)db);
+      const float quo = d / a;
+      if ((f2bits(quo) & 0x7f800000u) == 0x7f800000u) continue;   /* overflow: inf both ways */
+      bad += bf16_rn(quo) != bf16_rn(d * ra);
+      ++total;
+    }
+  }
+  printf("any ratio: %lld quotients, %lld mismatches\n", total, bad);
+  return bad != 0;
+}
+
 int main(int argc, char** argv) {
   if (argc > 1 && strcmp(argv[1], "addsub") == 0) return check_addsub();
+  if (argc > 1 && strcmp(argv[1], "anyratio") == 0) return check_anyratio();
   long long bad = 0, total = 0;
   /* a: every positive bf16 with exponent in [-100, 100]  (biased 27 .. 227) */
 #pragma omp parallel for reduction(+ : bad, total) schedule(dynamic, 64)

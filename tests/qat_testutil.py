@@ -113,3 +113,32 @@ def fuzz_cases(seed: int, n_cases: int = 6):
         g = torch.randn(*shape, generator=gen).to(DTYPES[dtype])
         what = (seed, case, dtype, shape, "sym" if sym else "asym", bits, lw, scale)
         yield what, dtype, sym, bits, lw, x, g
+
+
+def lowbit_edge_cases():
+    """Weights for the W1 / W2 path: LLaMA-like and ragged shapes with an all-zero row, +-inf, NaN,
+    -0.0 and magnitudes spread over 2^40.  Yields (dtype, w, bits, layerwise); shared by the CPU test
+    that pins the oracle to the live reference and the GPU test that pins the kernels to the oracle."""
+    gen = torch.Generator().manual_seed(12)
+    for dtype in ("fp32", "bf16"):
+        for rows, cols in ((64, 4096), (16, 11008), (9, 1000), (5, 172), (7, 1023)):
+            w = (torch.randn(rows, cols, generator=gen) * 0.02).to(DTYPES[dtype])
+            w[0] = 0.0
+            w[1, :6] = torch.tensor([float("inf"), -float("inf"), 1e-30, -1e-30, -0.0, 3.0]).to(w.dtype)
+            w[2, 3] = float("nan")
+            w[3, ::7] *= 1e6
+            w[4, ::5] *= 1e-6
+            for bits in (1, 2):
+                for lw in (False, True):
+                    yield dtype, w, bits, lw
+
+
+def lowbit_close(got: np.ndarray, ref: np.ndarray, dtype: str) -> bool:
+    """bf16: bit for bit.  fp32: same NaN / inf pattern and 2e-6 relative (mean|w| summation order)."""
+    if dtype == "bf16":
+        return f32_mismatches(got, ref) == 0
+    with np.errstate(all="ignore"):
+        if not (np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.isfinite(got), np.isfinite(ref))):
+            return False
+        ok = np.isfinite(ref)
+        return bool((np.abs(got[ok] - ref[ok]) / (np.abs(ref[ok]) + 1e-30)).max(initial=0.0) < 2e-6)

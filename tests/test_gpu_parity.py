@@ -438,6 +438,18 @@ def test_lowbit_weight_vs_reference_goldens(dtype):
             assert np.nanmax(rel) < 2e-6, (k, np.nanmax(rel))
 
 
+def test_lowbit_weight_edge_rows_and_shapes_vs_oracle():
+    """W1 / W2 weight path (qat_testutil.lowbit_edge_cases: edge rows, LLaMA-like and ragged shapes,
+    row-wise and layerwise) through the one-pass row kernel, its packed-bf16 chain, the
+    exact-division fallback (scale 0 / inf / NaN rows) and the two-pass path (odd width, layerwise)."""
+    from llm_qat_b200.utils_quant import _LowBitWeight
+
+    for dtype, w, bits, lw in U.lowbit_edge_cases():
+        got = U.tensor_to_f32(_LowBitWeight.apply(w.cuda(), bits, lw))
+        ref = qo.lowbit_weight(U.tensor_to_f32(w), bits, lw, dtype)["w_eff"]
+        assert U.lowbit_close(got, ref, dtype), (dtype, tuple(w.shape), bits, lw)
+
+
 # --------------------------------------------------------------- K4: tcgen05 GEMM
 @pytest.mark.parametrize("T,N,K", [(128, 256, 128), (256, 512, 4096), (200, 264, 1040), (8, 80, 192),
                                    (1024, 11008, 4096), (300, 520, 2064), (2048, 4096, 11008)])

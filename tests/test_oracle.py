@@ -125,7 +125,7 @@ def test_bf16_reciprocal_quotient_proof(tmp_path):
     """The packed-bf16 AsymQuantizer chain of K2 replaces the reference's two divisions by
     multiplications with per-row reciprocals and its add/sub by single-rounding bf16x2
     instructions.  oracle/proofs/bf16_quotient_by_reciprocal.c checks both claims exhaustively
-    (4.2e8 quotients; 4.26e9 add/sub pairs): compile and run it."""
+    (4.3e8 quotients; 4.26e9 add/sub pairs; 7.6e8 quotients of arbitrary ratio for the W1/W2 path): compile and run it."""
     import shutil
     import subprocess
 
@@ -135,7 +135,7 @@ def test_bf16_reciprocal_quotient_proof(tmp_path):
                        "bf16_quotient_by_reciprocal.c")
     exe = str(tmp_path / "bf16q")
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", src, "-o", exe], check=True)
-    for args in ([], ["addsub"]):
+    for args in ([], ["addsub"], ["anyratio"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout + r.stderr
 
@@ -168,3 +168,39 @@ def test_oracle_fuzz_matches_live_reference():
             assert qo.count_mismatch(U.tensor_to_f32(xi.grad), gref) == 0, what
             n += 1
     assert n == 72
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only exists in the build container")
+def test_oracle_lowbit_edge_cases_match_live_reference(monkeypatch):
+    """The oracle's W1 / W2 weight path against the UNMODIFIED reference on the edge-row cases the GPU
+    test uses; the effective weight is captured where QuantizeLinear.forward hands it to F.linear."""
+    import sys
+
+    import torch
+    import torch.nn as nn
+
+    sys.dont_write_bytecode = True
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import importlib
+
+    uq = importlib.import_module("models.utils_quant")
+    captured = {}
+    orig = nn.functional.linear
+
+    def capture(inp, weight, *a, **k):
+        captured["w"] = weight.detach().clone()
+        return orig(inp, weight, *a, **k)
+
+    monkeypatch.setattr(nn.functional, "linear", capture)
+    n = 0
+    for dtype, w, bits, lw in U.lowbit_edge_cases():
+        rows, cols = w.shape
+        lin = uq.QuantizeLinear(cols, rows, w_bits=bits, a_bits=32, weight_layerwise=lw).to(w.dtype)
+        with torch.no_grad():
+            lin.weight.copy_(w)
+        lin(torch.zeros(1, cols, dtype=w.dtype))
+        ref = qo.lowbit_weight(U.tensor_to_f32(w), bits, lw, dtype)["w_eff"]
+        assert U.lowbit_close(U.tensor_to_f32(captured["w"]), ref, dtype), (dtype, rows, cols, bits, lw)
+        n += 1
+    assert n == 40
