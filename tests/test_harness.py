@@ -261,3 +261,42 @@ print("ok", len(keys))
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("autocast", [False, True])
+def test_training_trajectory_matches_the_reference_chain(autocast, monkeypatch):
+    """30 QAT steps (teacher forward, student forward, KL loss, backward through gradient
+    checkpointing, AdamW) of a small LLaMA on three L1s with identical init and data.  Every kernel of
+    the unfused product path is bit-exact and everything else is the same torch op on the same GPU,
+    so its loss trajectory must be IDENTICAL to the reference chain's, step for step — with and
+    without the Trainer's autocast context.  The integer-grid path must track it closely."""
+    import llm_qat_b200
+
+    cfg = H.QatConfig(hidden_size=256, intermediate_size=688, num_attention_heads=4, num_hidden_layers=2,
+                      vocab_size=512, max_position_embeddings=128, w_bits=4, a_bits=8, kv_bits=4)
+
+    def run(quant, fused):
+        monkeypatch.setenv("QAT_B200_FUSED_LINEAR", fused)
+        torch.manual_seed(0)
+        student = H.CausalLM(cfg, quant).bfloat16().cuda()
+        teacher = H.build_teacher(cfg).bfloat16().cuda()
+        teacher.load_state_dict(student.state_dict())
+        with torch.no_grad():                         # make the student differ from its teacher
+            for p in student.parameters():
+                p.add_(torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())).to(p).mul_(0.01))
+        opt = torch.optim.AdamW(student.parameters(), lr=1e-3)
+        g = torch.Generator().manual_seed(99)
+        losses = []
+        for _ in range(30):
+            ids = torch.randint(0, cfg.vocab_size, (2, 64), generator=g).cuda()
+            losses.append(float(H.qat_step(student.train(), teacher, ids, opt, autocast=autocast)))
+        return losses
+
+    ref = run(R, "0")
+    unfused = run(llm_qat_b200.utils_quant, "0")
+    fused = run(llm_qat_b200.utils_quant, "1")
+    assert all(np.isfinite(ref)) and ref[-1] < ref[0]          # it trains
+    assert unfused == ref, [(i, a, b) for i, (a, b) in enumerate(zip(unfused, ref)) if a != b][:3]
+    rel = max(abs(a - b) / abs(b) for a, b in zip(fused, ref))
+    assert rel < 0.15 and abs(fused[-1] - ref[-1]) / ref[-1] < 0.15, (rel, fused[-3:], ref[-3:])
