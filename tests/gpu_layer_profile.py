@@ -4,6 +4,9 @@ torch.profiler kernel table for the product (fused) and the reference eager path
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import faulthandler
+# one run of this tool under torch.profiler (CUPTI tracing) with programmatic dependent launch on did not
+# return (not reproduced in five later runs, tests/gpu_profiler_check.py passes): trace with plain stream order
+os.environ.setdefault("QAT_B200_PDL", "0")
 faulthandler.dump_traceback_later(int(os.environ.get('PROFILE_TOOL_TIMEOUT', '240')), exit=True)   # a stuck run reports where
 import torch
 from torch.profiler import profile, ProfilerActivity
