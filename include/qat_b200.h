@@ -167,6 +167,25 @@ int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, int8_t* qx, f
 int qat_dequant_codes(const int8_t* codes, const float* row_e, void* out, int64_t rows, int64_t cols,
                       int dtype, void* stream);
 
+/*
+ * QuantizeLinear backward contractions — what autograd runs for utils_quant.py:250
+ * (two cuBLAS GEMMs) with the STE clip mask of utils_quant.py:83-87 fused into the epilogue.
+ *   out[m, n] = pass(m, n) * sum_k A(m, k) * B(n, k)          bf16 operands, fp32 accumulation
+ * a_mn_major = 0: A is row-major [M, K];  1: A is row-major [K, M]   (read in place, no transpose)
+ * b_mn_major = 0: B is row-major [N, K];  1: B is row-major [K, N]
+ *   dgrad  gx[T,K] = g[T,N] . Wq[N,K]    -> M=T, N=K_in, K=N_out, a_mn_major=0, b_mn_major=1
+ *   wgrad  gw[N,K] = g[T,N]^T . xq[T,K]  -> M=N_out, N=K_in, K=T, a_mn_major=1, b_mn_major=1
+ * mask (optional): packed pass-mask over the flattened [M, N] output, bit i%8 of byte i/8 (what
+ * qat_sym_fwd emits); masked-out elements are written as 0.  out: bf16 or fp32 per out_dtype.
+ * The contiguous dimension of each operand must be a multiple of 8 elements (TMA pitch).
+ * cta_group: 0 = choose, 1 = 128x256 tiles, 2 = CTA pairs on 256x256 tiles.
+ * tcgen05.mma kind::f16, TMEM accumulators, TMA-fed (MN-major shared-memory descriptors).
+ */
+int qat_gemm_bf16(const void* a, const void* b, void* out, const uint8_t* mask, int64_t M, int64_t N,
+                  int64_t K, int a_mn_major, int b_mn_major, int out_dtype, int cta_group, void* stream);
+/* Test hook: override the MN-major descriptor strides (bytes); 0, 0 restores the canonical ones. */
+int qat_gemm_bf16_debug_strides(uint32_t lbo_bytes, uint32_t sbo_bytes);
+
 /* Host-buffer convenience entry points (pinned or pageable host memory):
  * copy in, run, copy out on `stream`; `dev_scratch` must hold
  * qat_host_scratch_bytes(...) bytes of device memory. */

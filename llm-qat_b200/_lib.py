@@ -50,6 +50,9 @@ def _declare(lib):
         "qat_qlinear_fused_fwd": (I, [P, P, P, P, P, P, P, P, P, L, L, L, I, I, I, F, F, I, I, P]),
         # codes, row_e, out, rows, cols, dtype, stream
         "qat_dequant_codes": (I, [P, P, P, L, L, I, P]),
+        # a, b, out, mask, M, N, K, a_mn, b_mn, out_dtype, cta_group, stream
+        "qat_gemm_bf16": (I, [P, P, P, P, L, L, L, I, I, I, I, P]),
+        "qat_gemm_bf16_debug_strides": (I, [ctypes.c_uint32, ctypes.c_uint32]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
         "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),
