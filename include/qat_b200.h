@@ -46,7 +46,7 @@ extern "C" {
 
 /* optional integer-code output */
 #define QAT_CODES_NONE 0
-#define QAT_CODES_I8 1  /* saturating to [-127,127] (Sym) / [0,255] as uint8 (Asym); NaN -> 0.  GEMM feed. */
+#define QAT_CODES_I8 1  /* saturating to [-128,127] (Sym) / [0,255] as uint8 (Asym); NaN -> 0.  GEMM feed. */
 #define QAT_CODES_I16 2 /* exact; NaN -> INT16_MIN.  What parity tests compare. */
 
 /* error codes (cudaError_t values are passed through unchanged, all < 1000) */
@@ -95,6 +95,18 @@ int qat_sym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row_
 int qat_asym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row_a, float* row_b,
                  uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
                  int bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * How AsymQuantizer divides the code by S = 2^bits - 1 (utils_quant.py:146, `.div(s)` with a Python
+ * int): QAT_ASYM_DIV_TRUE (default) is the IEEE division torch's CPU kernel performs — BASELINE
+ * configs[0] names torch CPU, and the oracle follows it; QAT_ASYM_DIV_RECIP multiplies by fl(1/S), which
+ * is what ATen's CUDA kernel does for a CPU-scalar divisor, so fp32 results then match the reference
+ * run eagerly on a GPU bit for bit (33 % of fp32 elements differ between the two; bf16 results are
+ * identical for bits <= 8).  Process-wide; also settable once through QAT_B200_ASYM_DIV=cpu|cuda.
+ */
+#define QAT_ASYM_DIV_TRUE 0
+#define QAT_ASYM_DIV_RECIP 1
+int qat_set_asym_div(int mode);
 
 /*
  * SymQuantizer.backward / AsymQuantizer.backward — utils_quant.py:77-87, 152-162.
@@ -152,6 +164,10 @@ int qat_set_gemm_cta_group(int cta_group);
  * qx/ex/mx and qw/ew/mw receive the int8 codes, dequant divisors and packed STE
  * masks (mx / mw may be NULL); reuse_x / reuse_w != 0 skip a quantization whose
  * outputs the caller still holds.  K % 16 == 0, 2 <= bits <= 8.
+ * Deviation from the reference, plain-bf16 8-bit operands only: bf16 rounding of x*s can give the
+ * code +128 for a row's largest elements (fp32 tensors and dtype QAT_BF16_AMP — the recipe's
+ * autocast chain — cannot); the int8 feed carries 127 for them (-128 is exact), i.e. a 1/128 change
+ * of those terms of the dot product.  qat_sym_fwd with QAT_CODES_I16 returns the exact codes.
  */
 int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, int8_t* qx, float* ex, uint8_t* mx,
                           int8_t* qw, float* ew, uint8_t* mw, int64_t T, int64_t N, int64_t K, int dtype,

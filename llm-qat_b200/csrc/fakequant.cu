@@ -32,7 +32,7 @@ struct FwdParams {
   int64_t rows;
   int64_t cols;
   int64_t nvec;  // vectors (VEC) or elements (scalar path) per row
-  float qmax;    // Sym: Q = 2^(bits-1)-1     Asym: S = 2^bits-1
+  float qmax;    // Sym: Q = 2^(bits-1)-1     Asym: S = 2^bits-1, negated in the QAT_ASYM_DIV_RECIP mode
   int group;     // threads cooperating on one row (power of two, >= 32)
   int log2_group;
   // long-row path
@@ -286,7 +286,9 @@ struct ScaleOf<DT, false> {
   using type = AsymScale<DT>;
   static __device__ __forceinline__ type make(const RowStat& r, float qmax) {
     type s;
-    s.derive(r.mx, r.mn, r.nan != 0u, qmax);
+    // a negative qmax carries the "multiply by fl(1/S)" mode of qat_set_asym_div (FwdParams::qmax)
+    s.derive(r.mx, r.mn, r.nan != 0u, fabsf(qmax));
+    s.mulS = qmax < 0.f;
     return s;
   }
   static __device__ __forceinline__ float st0(const type& s) { return s.a; }
@@ -324,7 +326,8 @@ __device__ __forceinline__ typename ScaleOf<DT, SYM>::type warp_derive_scale(con
     sc.a = __shfl_sync(kFull, sc.a, 0);
     sc.beta = __shfl_sync(kFull, sc.beta, 0);
     sc.ra.r1 = __shfl_sync(kFull, sc.ra.r1, 0);
-    sc.S = qmax;
+    sc.S = fabsf(qmax);
+    sc.mulS = qmax < 0.f;
     sc.rS = __shfl_sync(kFull, sc.rS, 0);
     sc.ra_rn = __shfl_sync(kFull, sc.ra_rn, 0);
     sc.finish();
@@ -855,6 +858,17 @@ float round_to_dtype(float v, int dtype) {
   return __bfloat162float(__float2bfloat16_rn(v));
 }
 
+// AsymQuantizer's `.div(S)`: 0 = true division (torch CPU), 1 = multiply by fl(1/S) (ATen CUDA).
+// -1: read QAT_B200_ASYM_DIV ("cuda" selects 1) on first use.
+int g_asym_div = -1;
+int asym_div_mode() {
+  if (g_asym_div < 0) {
+    const char* v = getenv("QAT_B200_ASYM_DIV");
+    g_asym_div = (v != nullptr && (v[0] == 'c' || v[0] == 'C') && (v[1] == 'u' || v[1] == 'U')) ? 1 : 0;
+  }
+  return g_asym_div;
+}
+
 template <bool SYM>
 int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, float* st1,
               uint8_t* mask, float lo, float hi, int64_t rows, int64_t cols, int dtype, int bits,
@@ -908,6 +922,7 @@ int fwd_entry(const void* x, void* y, void* codes, int codes_kind, float* st0, f
   p.nvec = pl.nvec;
   // the reference's Python int, converted to the fp32 op scalar (round to nearest)
   p.qmax = SYM ? (float)((1ll << (bits - 1)) - 1) : (float)((1ll << bits) - 1);
+  if (!SYM && asym_div_mode() == 1) p.qmax = -p.qmax;   // see ScaleOf<DT, false>::make
   p.group = pl.group;
   p.log2_group = 0;
   while ((1 << p.log2_group) < pl.group) ++p.log2_group;
@@ -963,6 +978,12 @@ int qat_asym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row
                  int bits, void* workspace, size_t workspace_bytes, void* stream) {
   return qat::fwd_entry<false>(x, y, codes, codes_kind, row_a, row_b, mask, clip_lo, clip_hi, rows,
                                cols, dtype, bits, workspace, workspace_bytes, stream);
+}
+
+int qat_set_asym_div(int mode) {
+  QAT_CHECK_ARG(mode == QAT_ASYM_DIV_TRUE || mode == QAT_ASYM_DIV_RECIP, "mode must be QAT_ASYM_DIV_TRUE or QAT_ASYM_DIV_RECIP");
+  qat::g_asym_div = mode;
+  return QAT_OK;
 }
 
 }  // extern "C"

@@ -24,8 +24,22 @@ Run-time knobs (environment; signatures stay the reference's):
                               accumulation): also reuse across plain forwards, keyed on the parameter's
                               (data_ptr, _version) — NOT safe under wrappers that rewrite parameter
                               storage behind that key (FSDP use_orig_params=True).  0: no reuse.
+  QAT_B200_WEIGHT_REUSE=0|1   0: never keep a module's weight codes between its forward and its
+                              backward (1.125 B per weight element per live layer — under FSDP
+                              full_shard that is unsharded memory); q/k/v and gate/up still share
+                              their activation codes.  Default 1.
   QAT_B200_FUSED_LINEAR=0|1   QuantizeLinear uses the integer-grid tcgen05 GEMM (default 1, taken
                               when shapes/dtypes allow) or the fake-quant kernels + F.linear (0).
+                              The int8 operand feed holds codes in [-128, 127]: a plain-bf16 (no
+                              autocast) 8-bit activation row whose largest element rounds to the code
+                              +128 (bf16 arithmetic can produce it, fp32 and the autocast chain cannot)
+                              carries 127 for that element — at most the row's maxima, a 1/128 change of
+                              one term of the dot product.  0 gives the reference's operands exactly.
+  QAT_B200_ASYM_DIV=cpu|cuda  AsymQuantizer's `.div(S)` (utils_quant.py:146): "cpu" (default) is the true
+                              division torch's CPU kernel performs (BASELINE configs[0] names torch CPU);
+                              "cuda" multiplies by fl(1/S) like ATen's CUDA kernel for a Python-scalar
+                              divisor, reproducing the reference's eager-GPU bits for fp32 tensors
+                              (bf16 results are identical under both).
 """
 from __future__ import annotations
 
@@ -285,6 +299,11 @@ class _LowBitWeight(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------ fused linear
+# longest row qat_sym_fwd handles without a workspace (register-resident: 8192 16-byte vectors of
+# fp32; bf16 rows could be twice as long — the smaller bound keeps one rule)
+_MAX_FEED_COLS = 32768
+
+
 def _fused_linear_enabled() -> bool:
     return os.environ.get("QAT_B200_FUSED_LINEAR", "1") != "0"
 
@@ -292,6 +311,10 @@ def _fused_linear_enabled() -> bool:
 def _cache_mode() -> int:
     v = os.environ.get("QAT_B200_CACHE", "1")
     return 0 if v == "0" else 2 if v == "2" else 1
+
+
+def _weight_reuse_enabled() -> bool:
+    return os.environ.get("QAT_B200_WEIGHT_REUSE", "1") != "0"
 
 
 def _in_backward_pass() -> bool:
@@ -320,9 +343,9 @@ def _feed_views(blob: torch.Tensor, rows: int, cols: int):
 
 # Single-slot memo of the last quantized activation per device: q/k/v (and gate/up)
 # receive the very same tensor OBJECT, so its codes are produced once (SURVEY.md
-# 8f-2).  A hit needs that identity (weak reference) plus an unchanged _version;
-# the slot also pins the detached view, so the storage cannot be recycled while
-# the entry is live.
+# 8f-2).  A hit needs that identity (weak reference: a live tensor object keeps its
+# storage) plus an unchanged data_ptr and _version.  The slot holds only the codes
+# blob, never the activation, and is dropped by the first backward of the step.
 _ACT_SLOT: dict = {}
 
 
@@ -345,6 +368,8 @@ class _QuantLinearFn(torch.autograd.Function):
     def forward(ctx, input, weight, w_bits, a_bits, owner):
         K = input.shape[-1]
         N = weight.shape[0]
+        if weight.dim() != 2 or weight.shape[1] != K:
+            raise RuntimeError(f"QuantizeLinear: input features {K} do not match weight {tuple(weight.shape)}")
         x2 = input.detach()
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -383,9 +408,15 @@ class _QuantLinearFn(torch.autograd.Function):
                 reuse_x, reuse_w, stream)
         check(rc, "qat_qlinear_fused_fwd")
         if mode:
-            _ACT_SLOT[dev.index] = (xkey, x2, xblob, weakref.ref(input))
-            if owner is not None:
+            _ACT_SLOT[dev.index] = (xkey, None, xblob, weakref.ref(input))
+            # Weight codes are kept on the module only when a consumer can follow: a gradient-
+            # checkpoint recompute of this step (mode 1: the module is training; cleared by its own
+            # backward) or any later forward of frozen weights (mode 2).  Evaluation / no_grad
+            # inference in mode 1 keeps nothing.
+            if owner is not None and _weight_reuse_enabled() and (mode == 2 or owner.training):
                 owner._qat_wfeed = (wkey, wblob)
+            elif owner is not None and getattr(owner, "_qat_wfeed", None) is not None:
+                owner._qat_wfeed = None
         ctx.save_for_backward(xblob, wblob)
         ctx.owner_ref = weakref.ref(owner) if (owner is not None and mode == 1) else None
         ctx.dims = (T, N, K)
@@ -401,37 +432,57 @@ class _QuantLinearFn(torch.autograd.Function):
         if not g2.is_contiguous():
             g2 = g2.contiguous()
         dev, dtype = g2.device, ctx.dtype
+        if g2.dtype != dtype:
+            g2 = g2.to(dtype)
         dt = _DTYPES[dtype]
         L = _lib.lib()
         xb, wb = xblob.data_ptr(), wblob.data_ptr()
         xe, xm, _ = _feed_layout(T, K)
         we, wm, _ = _feed_layout(N, K)
+        # bf16: both contractions run on this library's tcgen05 kernel (qat_gemm_bf16), reading the
+        # operands where they lie (W_q [N,K] and x_q [T,K] as MN-major B, g [T,N] as K-major /
+        # MN-major A) with the STE pass-mask applied to the fp32 accumulator in the epilogue.
+        # fp32 modules keep the library GEMM + mask kernel.
+        own = dtype == torch.bfloat16 and N % 8 == 0 and K % 8 == 0 and g2.data_ptr() % 16 == 0
         gx = gw = None
         with _on(dev):
             stream = _stream_ptr(dev)
             if ctx.needs_input_grad[0]:
                 wq = torch.empty((N, K), dtype=dtype, device=dev)           # == the reference's fake-quant W
                 check(L.qat_dequant_codes(wb, wb + we, wq.data_ptr(), N, K, dt, stream), "qat_dequant_codes")
-                t = torch.mm(g2, wq)
+                if own:
+                    gx = torch.empty((T, K), dtype=dtype, device=dev)
+                    check(L.qat_gemm_bf16(g2.data_ptr(), wq.data_ptr(), gx.data_ptr(), xb + xm, T, K, N, 0, 1,
+                                          dt, 0, stream), "qat_gemm_bf16 (dgrad)")
+                else:
+                    t = torch.mm(g2, wq)
+                    gx = torch.empty_like(t)
+                    check(L.qat_ste_bwd_from_mask(t.data_ptr(), xb + xm, gx.data_ptr(), T * K, dt, stream),
+                          "qat_ste_bwd_from_mask")
                 del wq
-                gx = torch.empty_like(t)
-                check(L.qat_ste_bwd_from_mask(t.data_ptr(), xb + xm, gx.data_ptr(), T * K, dt, stream),
-                      "qat_ste_bwd_from_mask")
                 gx = gx.view(ctx.in_shape)
             if ctx.needs_input_grad[1]:
                 xq = torch.empty((T, K), dtype=dtype, device=dev)           # == the reference's fake-quant x
                 check(L.qat_dequant_codes(xb, xb + xe, xq.data_ptr(), T, K, dt, stream), "qat_dequant_codes")
-                t = torch.mm(g2.t(), xq)
+                if own:
+                    gw = torch.empty((N, K), dtype=dtype, device=dev)
+                    check(L.qat_gemm_bf16(g2.data_ptr(), xq.data_ptr(), gw.data_ptr(), wb + wm, N, K, T, 1, 1,
+                                          dt, 0, stream), "qat_gemm_bf16 (wgrad)")
+                else:
+                    t = torch.mm(g2.t(), xq)
+                    gw = torch.empty_like(t)
+                    check(L.qat_ste_bwd_from_mask(t.data_ptr(), wb + wm, gw.data_ptr(), N * K, dt, stream),
+                          "qat_ste_bwd_from_mask")
                 del xq
-                gw = torch.empty_like(t)
-                check(L.qat_ste_bwd_from_mask(t.data_ptr(), wb + wm, gw.data_ptr(), N * K, dt, stream),
-                      "qat_ste_bwd_from_mask")
         # mode 1 keeps a module's codes only from its forward to its backward (for the checkpoint
         # recompute in between): 1.125 B per weight element must not sit in HBM through the
         # optimizer step
         owner = ctx.owner_ref() if ctx.owner_ref is not None else None
         if owner is not None:
             owner._qat_wfeed = None
+        # the shared activation codes are dead once a consumer's backward runs (the step's
+        # forwards are over); do not pin the last blob past the step
+        _ACT_SLOT.pop(dev.index, None)
         return gx, gw, None, None, None
 
 
@@ -496,7 +547,10 @@ class QuantizeLinear(nn.Linear):
             and input_.dtype == self.weight.dtype
             and 1 <= input_.dim() <= 3
             and input_.shape[-1] % 16 == 0
+            and input_.shape[-1] == self.weight.shape[1]   # else F.linear raises its usual shape error
+            and input_.shape[-1] <= _MAX_FEED_COLS          # rows the feed kernel keeps in registers
             and input_.numel() > 0
+            and input_.data_ptr() % 16 == 0 and self.weight.data_ptr() % 16 == 0
             # under autocast to another dtype the reference's F.linear casts its operands and
             # returns that dtype: leave that case to the unfused path, which does exactly that
             and not (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") != input_.dtype)

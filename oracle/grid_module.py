@@ -46,8 +46,9 @@ class _GridLinear(torch.autograd.Function):
         x2 = x.reshape(-1, K)
         qx, ex = sym_codes(x2, a_bits)
         qw, ew = sym_codes(w, w_bits)
-        # int8 feed: a bf16 A8 code can reach +-128; the product saturates it
-        qx, qw = qx.clamp(-127, 127), qw.clamp(-127, 127)
+        # int8 feed: a bf16 A8 code can reach +-128; the product carries -128
+        # exactly and saturates +128 to 127
+        qx, qw = qx.clamp(-128, 127), qw.clamp(-128, 127)
         ctx.save_for_backward(x, w, qx.div(ex), qw.div(ew))          # the reference's fake-quant tensors
         dot = qx.double() @ qw.double().t()
         rx, rw = 1.0 / ex.float(), 1.0 / ew.float()

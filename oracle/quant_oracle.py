@@ -138,8 +138,11 @@ def sym_forward(x: np.ndarray, num_bits: int, layerwise: bool = False, dtype: st
 # --------------------------------------------------------------------------
 # AsymQuantizer.forward  (utils_quant.py:96-149)
 # --------------------------------------------------------------------------
-def asym_forward(x: np.ndarray, num_bits: int, layerwise: bool = False, dtype: str = "fp32"):
-    """Returns dict(y, codes, a, beta) — a = alpha + 1e-8 per row, beta = row min."""
+def asym_forward(x: np.ndarray, num_bits: int, layerwise: bool = False, dtype: str = "fp32", div: str = "cpu"):
+    """Returns dict(y, codes, a, beta) — a = alpha + 1e-8 per row, beta = row min.
+    ``div``: how `.div(s)` (:146, s a Python int) is evaluated — "cpu": IEEE division (torch's CPU
+    kernel; the pinned default), "cuda": multiply by fl32(1/S), ATen's CUDA kernel for a CPU-scalar
+    divisor (pinned on the GPU box against the reference chain run eagerly on CUDA)."""
     fl = _fl(dtype)
     x = np.asarray(x, dtype=F32)
     x2 = as_rows(x, layerwise)
@@ -152,7 +155,10 @@ def asym_forward(x: np.ndarray, num_bits: int, layerwise: bool = False, dtype: s
         a = fl(alpha + EPS_ASYM)                 # :144
         n = fl(fl(x2 - beta) / a)                # :144
         q = np.rint(fl(n * S)).astype(F32)       # :146
-        u = fl(q / S)                            # :146  .div(s) — true division
+        if div == "cuda":
+            u = fl(q * (F32(1.0) / S))           # :146  .div(s) — ATen CUDA: a * (1 / b)
+        else:
+            u = fl(q / S)                        # :146  .div(s) — true division
         y = fl(fl(u * a) + beta)                 # :147  two roundings, no FMA
     return {
         "y": y.reshape(x.shape),
