@@ -202,6 +202,24 @@ int qat_gemm_bf16(const void* a, const void* b, void* out, const uint8_t* mask, 
 /* Test hook: override the MN-major descriptor strides (bytes); 0, 0 restores the canonical ones. */
 int qat_gemm_bf16_debug_strides(uint32_t lbo_bytes, uint32_t sbo_bytes);
 
+/*
+ * Fused causal attention on tcgen05 — replaces the eager block of
+ * models/modeling_llama_quant.py:352-377 (QK^T / sqrt(d), + mask, max(finfo.min), fp32 softmax,
+ * cast, . V) and its autograd backward, for the causal mask of :60-92; no [b, h, s, s] tensor is
+ * materialised.  K and V are consumed as the K/V fake-quant (:320-327) and RoPE left them.
+ *   q, k, v, o, d_o, dq, dk, dv : bf16 [B, S, H, head_dim] (== [b, s, hidden] of the projections), head_dim == 128
+ *   lse   : fp32 [B, H, S], natural-log sum-exp of the scaled scores (saved for backward; may be NULL in fwd)
+ *   delta : fp32 [B, H, S] scratch of the backward (rowsum(dO * O))
+ *   causal != 0: key j is visible to query i iff j <= i;  0: every key is visible
+ * Scores, softmax and accumulation are fp32; P is rounded to bf16 before P.V like the reference's
+ * `.to(query_states.dtype)`.  Agreement with the eager chain: <= 1e-2 relative (bf16).
+ */
+int qat_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
+                 int head_dim, float softmax_scale, int causal, void* stream);
+int qat_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                 float* delta, void* dq, void* dk, void* dv, int B, int S, int H, int head_dim,
+                 float softmax_scale, int causal, void* stream);
+
 /* Host-buffer convenience entry points (pinned or pageable host memory):
  * copy in, run, copy out on `stream`; `dev_scratch` must hold
  * qat_host_scratch_bytes(...) bytes of device memory. */

@@ -54,6 +54,10 @@ def _declare(lib):
         # a, b, out, mask, M, N, K, a_mn, b_mn, out_dtype, cta_group, stream
         "qat_gemm_bf16": (I, [P, P, P, P, L, L, L, I, I, I, I, P]),
         "qat_gemm_bf16_debug_strides": (I, [ctypes.c_uint32, ctypes.c_uint32]),
+        # q, k, v, o, lse, B, S, H, D, scale, causal, stream
+        "qat_attn_fwd": (I, [P, P, P, P, P, I, I, I, I, F, I, P]),
+        # q, k, v, o, do, lse, delta, dq, dk, dv, B, S, H, D, scale, causal, stream
+        "qat_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
         "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),
