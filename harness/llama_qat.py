@@ -54,24 +54,37 @@ class QatConfig:
 
 
 class RMSNorm(nn.Module):
+    """LlamaRMSNorm (:112-129), same attribute names."""
+
     def __init__(self, dim, eps):
         super().__init__()
         self.weight = nn.Parameter(torch.ones(dim))
-        self.eps = eps
+        self.variance_epsilon = eps
 
     def forward(self, h):
         var = h.to(torch.float32).pow(2).mean(-1, keepdim=True)
-        h = h * torch.rsqrt(var + self.eps)
+        h = h * torch.rsqrt(var + self.variance_epsilon)
         if self.weight.dtype in (torch.float16, torch.bfloat16):
             h = h.to(self.weight.dtype)
         return self.weight * h
 
 
-def _rope_tables(head_dim, n_pos, device, base=10000.0):
-    inv = 1.0 / (base ** (torch.arange(0, head_dim, 2, device=device).float() / head_dim))
-    freqs = torch.outer(torch.arange(n_pos, device=device, dtype=inv.dtype), inv)
-    emb = torch.cat((freqs, freqs), dim=-1)
-    return emb.cos(), emb.sin()
+class RotaryEmbedding(nn.Module):
+    """LlamaRotaryEmbedding (:132-171): fp32 cos / sin caches [1, 1, max_pos, dim], returned in x's dtype."""
+
+    def __init__(self, dim, max_position_embeddings=2048, base=10000, device=None):
+        super().__init__()
+        inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2).float().to(device) / dim))
+        self.register_buffer("inv_freq", inv_freq, persistent=False)
+        t = torch.arange(max_position_embeddings, device=inv_freq.device, dtype=inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, inv_freq)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.register_buffer("cos_cached", emb.cos()[None, None, :, :], persistent=False)
+        self.register_buffer("sin_cached", emb.sin()[None, None, :, :], persistent=False)
+
+    def forward(self, x, seq_len=None):
+        return (self.cos_cached[:, :, :seq_len, ...].to(dtype=x.dtype),
+                self.sin_cached[:, :, :seq_len, ...].to(dtype=x.dtype))
 
 
 def _rotate_half(x):
@@ -79,42 +92,51 @@ def _rotate_half(x):
     return torch.cat((-x[..., half:], x[..., :half]), dim=-1)
 
 
+def _apply_rotary_pos_emb(q, k, cos, sin, position_ids):   # :181-196
+    cos = cos.squeeze(1).squeeze(0)[position_ids].unsqueeze(1)
+    sin = sin.squeeze(1).squeeze(0)[position_ids].unsqueeze(1)
+    return (q * cos) + (_rotate_half(q) * sin), (k * cos) + (_rotate_half(k) * sin)
+
+
 class Attention(nn.Module):
+    """LlamaAttention (:238-393) with the reference's attribute names and call signature, so that
+    llm_qat_b200.fuse_model treats it exactly like the reference's module."""
+
     def __init__(self, cfg: QatConfig, quant):
         super().__init__()
         H = cfg.hidden_size
-        self.n_heads, self.head_dim, self.kv_bits = cfg.num_attention_heads, H // cfg.num_attention_heads, cfg.kv_bits
+        self.hidden_size, self.num_heads = H, cfg.num_attention_heads
+        self.head_dim, self.kv_bits = H // cfg.num_attention_heads, cfg.kv_bits
+        self.max_position_embeddings = cfg.max_position_embeddings
         mk = lambda: quant.QuantizeLinear(H, H, bias=False, w_bits=cfg.w_bits, a_bits=cfg.a_bits)  # noqa: E731
         self.q_proj, self.k_proj, self.v_proj, self.o_proj = mk(), mk(), mk(), mk()
-        self.kv_quantizer = quant.SymQuantizer
-        self.clip_k = torch.tensor([-2.0, 2.0])
-        self.clip_v = torch.tensor([-2.0, 2.0])
-        self.max_pos = cfg.max_position_embeddings
+        self.act_quantizer_k = self.act_quantizer_v = quant.SymQuantizer
+        self.act_clip_val_k = torch.tensor([-2.0, 2.0])
+        self.act_clip_val_v = torch.tensor([-2.0, 2.0])
+        self.rotary_emb = RotaryEmbedding(self.head_dim, max_position_embeddings=cfg.max_position_embeddings)
 
-    def forward(self, h, mask, position_ids):
-        b, s, H = h.shape
-        q = self.q_proj(h).view(b, s, self.n_heads, self.head_dim).transpose(1, 2)
-        k = self.k_proj(h)
-        v = self.v_proj(h)
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
+                output_attentions=False, use_cache=False):
+        b, s, H = hidden_states.shape
+        q = self.q_proj(hidden_states).view(b, s, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.k_proj(hidden_states)
+        v = self.v_proj(hidden_states)
         if self.kv_bits < 32:   # per-token over all heads' channels, before the head split and RoPE
-            k = self.kv_quantizer.apply(k, self.clip_k, self.kv_bits, False)
-            v = self.kv_quantizer.apply(v, self.clip_v, self.kv_bits, False)
-        k = k.view(b, s, self.n_heads, self.head_dim).transpose(1, 2)
-        v = v.view(b, s, self.n_heads, self.head_dim).transpose(1, 2)
-        cos, sin = _rope_tables(self.head_dim, max(self.max_pos, s), h.device)
+            k = self.act_quantizer_k.apply(k, self.act_clip_val_k, self.kv_bits, False)
+            v = self.act_quantizer_v.apply(v, self.act_clip_val_v, self.kv_bits, False)
+        k = k.view(b, s, self.num_heads, self.head_dim).transpose(1, 2)
+        v = v.view(b, s, self.num_heads, self.head_dim).transpose(1, 2)
         # rotary_emb(value_states, ...) returns tables in V's dtype (:334) — fp32 under autocast, where
         # the K/V fake-quant returns float32
-        cos = cos.to(v.dtype)[position_ids].unsqueeze(1)
-        sin = sin.to(v.dtype)[position_ids].unsqueeze(1)
-        q = q * cos + _rotate_half(q) * sin
-        k = k * cos + _rotate_half(k) * sin
+        cos, sin = self.rotary_emb(v, seq_len=s)
+        q, k = _apply_rotary_pos_emb(q, k, cos, sin, position_ids)
         w = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(self.head_dim)
-        if mask is not None:
-            w = w + mask
+        if attention_mask is not None:
+            w = w + attention_mask
             w = torch.max(w, torch.tensor(torch.finfo(w.dtype).min, device=w.device))
         w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
         o = torch.matmul(w, v).transpose(1, 2).reshape(b, s, H)
-        return self.o_proj(o)
+        return self.o_proj(o), None, None
 
 
 class MLP(nn.Module):
@@ -124,9 +146,10 @@ class MLP(nn.Module):
         self.gate_proj = quant.QuantizeLinear(H, I, bias=False, w_bits=cfg.w_bits, a_bits=cfg.a_bits)
         self.down_proj = quant.QuantizeLinear(I, H, bias=False, w_bits=cfg.w_bits, a_bits=cfg.a_bits)
         self.up_proj = quant.QuantizeLinear(H, I, bias=False, w_bits=cfg.w_bits, a_bits=cfg.a_bits)
+        self.act_fn = nn.SiLU()
 
     def forward(self, x):
-        return self.down_proj(F.silu(self.gate_proj(x)) * self.up_proj(x))
+        return self.down_proj(self.act_fn(self.gate_proj(x)) * self.up_proj(x))
 
 
 class DecoderLayer(nn.Module):
@@ -138,7 +161,8 @@ class DecoderLayer(nn.Module):
         self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
 
     def forward(self, h, mask=None, position_ids=None):
-        h = h + self.self_attn(self.input_layernorm(h), mask, position_ids)
+        a, _, _ = self.self_attn(hidden_states=self.input_layernorm(h), attention_mask=mask, position_ids=position_ids)
+        h = h + a
         return h + self.mlp(self.post_attention_layernorm(h))
 
 
@@ -150,9 +174,10 @@ def causal_mask(b, s, dtype, device):
 
 class CausalLM(nn.Module):
     """embed -> N decoder layers (checkpointed when training) -> norm -> lm_head;
-    embed and lm_head are plain (unquantized), as in the reference (:581-583, :793)."""
+    embed and lm_head are plain (unquantized), as in the reference (:581-583, :793).
+    ``fused=True`` applies llm_qat_b200.fuse_model (attention / MLP / RMSNorm kernels, default off)."""
 
-    def __init__(self, cfg: QatConfig, quant, gradient_checkpointing=True):
+    def __init__(self, cfg: QatConfig, quant, gradient_checkpointing=True, fused=False):
         super().__init__()
         self.cfg = cfg
         self.embed_tokens = nn.Embedding(cfg.vocab_size, cfg.hidden_size)
@@ -161,6 +186,11 @@ class CausalLM(nn.Module):
         self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
         self.gradient_checkpointing = gradient_checkpointing
         self.apply(self._init)
+        self.fused = fused
+        if fused:
+            import llm_qat_b200
+
+            llm_qat_b200.fuse_model(self)
 
     def _init(self, m):
         if isinstance(m, nn.Linear):
@@ -172,6 +202,10 @@ class CausalLM(nn.Module):
         b, s = input_ids.shape
         h = self.embed_tokens(input_ids)
         mask = causal_mask(b, s, h.dtype, h.device)
+        if self.fused:   # what the patched _prepare_decoder_attention_mask does for the reference's LlamaModel
+            import llm_qat_b200
+
+            llm_qat_b200.mark_causal_mask(mask)
         pos = torch.arange(s, device=h.device)[None].expand(b, s)
         for layer in self.layers:
             if self.gradient_checkpointing and self.training and torch.is_grad_enabled():
@@ -195,9 +229,9 @@ class _PlainQuant:
         return nn.Linear(i, o, bias=False)
 
 
-def build_teacher(cfg: QatConfig):
+def build_teacher(cfg: QatConfig, fused=False):
     fp = QatConfig(**{**cfg.__dict__, "w_bits": 32, "a_bits": 32, "kv_bits": 32})
-    t = CausalLM(fp, _PlainQuant, gradient_checkpointing=False)
+    t = CausalLM(fp, _PlainQuant, gradient_checkpointing=False, fused=fused)
     for p in t.parameters():
         p.requires_grad_(False)
     return t.eval()
@@ -208,7 +242,7 @@ def kd_loss(student_logits, teacher_logits):
     return F.kl_div(F.log_softmax(student_logits, dim=2), F.softmax(teacher_logits, dim=2), reduction="batchmean")
 
 
-def qat_step(student, teacher, input_ids, optimizer, kd_loss_scale=1.0, autocast=False):
+def qat_step(student, teacher, input_ids, optimizer, kd_loss_scale=1.0, autocast=False, loss_fn=None):
     """One training step of compute_loss_train + backward + optimizer (kd_trainer.py:53-127).
     ``autocast=True`` mirrors the recipe: HF's Trainer (run_train.sh `--bf16 True`) computes the
     loss — teacher and student forward — inside torch.autocast(bfloat16) (kd_trainer.py:106)."""
@@ -217,7 +251,7 @@ def qat_step(student, teacher, input_ids, optimizer, kd_loss_scale=1.0, autocast
         with torch.no_grad():
             t_logits = teacher(input_ids)
         s_logits = student(input_ids)
-        loss = kd_loss_scale * kd_loss(s_logits, t_logits)
+        loss = kd_loss_scale * (loss_fn or kd_loss)(s_logits, t_logits)
     del t_logits, s_logits
     loss.backward()
     optimizer.step()

@@ -220,6 +220,67 @@ int qat_attn_bwd(const void* q, const void* k, const void* v, const void* o, con
                  float* delta, void* dq, void* dk, void* dv, int B, int S, int H, int head_dim,
                  float softmax_scale, int causal, void* stream);
 
+/*
+ * Logit-distillation loss — utils/kd_trainer.py:42-48:
+ *   loss = KLDivLoss(reduction="batchmean")(log_softmax(student, dim=2), softmax(teacher, dim=2))
+ *        = (1 / batch) * sum over rows and vocabulary of p_t (log p_t - log q_s),   fp32 arithmetic.
+ * student / teacher: [rows, V] logits (rows = batch * seq), fp32 or bf16 per `dtype`.
+ * fwd: loss (1 float), row_kl [rows] and row_stat [rows * 4] (scratch kept for bwd); one read of both.
+ * bwd: grad_student[r, v] = (softmax(student) - softmax(teacher)) * (*grad_loss) / batch, in `dtype`;
+ *      grad_loss is a DEVICE float (NULL = 1.0): no host synchronisation.
+ * Summation order differs from eager PyTorch's: agreement <= 1e-5 relative on the loss.
+ */
+int qat_kd_loss_fwd(const void* student, const void* teacher, float* loss, float* row_kl, float* row_stat,
+                    int64_t rows, int64_t V, int64_t batch, int dtype, void* stream);
+int qat_kd_loss_bwd(const void* student, const void* teacher, const float* row_stat, const float* grad_loss,
+                    void* grad_student, int64_t rows, int64_t V, int64_t batch, int dtype, void* stream);
+
+/*
+ * Producers of QuantizeLinear's inputs, fused with the per-token fake-quantization of what they produce
+ * (bf16 tensors; dtype = QAT_BF16, or QAT_BF16_AMP inside torch.autocast — see above).  codes / row_e / mask
+ * are exactly what qat_sym_fwd's GEMM-feed mode emits for the produced tensor (NULL codes: producer only).
+ *
+ * LlamaRMSNorm.forward — models/modeling_llama_quant.py:121-129:
+ *   y = weight * bf16( x * rsqrt(mean(x^2) + eps) );  rstd [rows] (fp32) is kept for the backward.
+ * qat_rmsnorm_bwd: grad_x [rows, cols] bf16, grad_weight [cols] bf16 (fixed-order column sums through
+ *   `workspace`, qat_rmsnorm_bwd_workspace_bytes).  cols % 8 == 0, cols <= 8192.
+ */
+int qat_rmsnorm_feed_fwd(const void* x, const void* weight, void* y, float* rstd, int8_t* codes, float* row_e,
+                         uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, float eps,
+                         int dtype, int bits, void* stream);
+size_t qat_rmsnorm_bwd_workspace_bytes(int64_t rows, int64_t cols);
+int qat_rmsnorm_bwd(const void* grad_y, const void* x, const void* weight, const float* rstd, void* grad_x,
+                    void* grad_weight, void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols,
+                    void* stream);
+/*
+ * LlamaMLP.forward's act_fn(gate_proj(x)) * up_proj(x) — models/modeling_llama_quant.py:235 (SiLU):
+ *   act = bf16(silu(gate)) * up, with the feed of `act` for down_proj.  cols % 8 == 0, cols <= 16384.
+ * qat_swiglu_bwd: elementwise, n = number of elements (multiple of 8).
+ */
+int qat_swiglu_feed_fwd(const void* gate, const void* up, void* act, int8_t* codes, float* row_e, uint8_t* mask,
+                        float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype, int bits, void* stream);
+int qat_swiglu_bwd(const void* grad_act, const void* gate, const void* up, void* grad_gate, void* grad_up, int64_t n,
+                   void* stream);
+/*
+ * The K/V fake-quant call site and the rotary embedding in one launch —
+ * models/modeling_llama_quant.py:320-341: key / value = SymQuantizer.apply(k_proj / v_proj output,
+ * [-2, 2], kv_bits, False) per token over all heads' channels (skipped when kv_bits >= 32), then
+ * apply_rotary_pos_emb on query and key (:174-196).  q, k, v and the outputs: bf16 [tokens, heads * 128];
+ * cos_table / sin_table: fp32 [max_pos, 128] (LlamaRotaryEmbedding's caches); position_ids int64 [tokens].
+ * k_mask / v_mask receive the packed STE pass-masks of the unquantized K / V.  The fake-quantized values
+ * are bit-identical to qat_sym_fwd's (same chain); under QAT_BF16_AMP K is rotated in fp32 and rounded
+ * once to bf16, as autocast's matmul cast does.
+ * qat_qkv_prep_bwd: gradients of the three inputs from those of the three outputs (RoPE transpose, STE masks).
+ */
+int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, void* q_out, void* k_out, void* v_out,
+                     uint8_t* k_mask, uint8_t* v_mask, const float* cos_table, const float* sin_table,
+                     const int64_t* position_ids, int64_t tokens, int heads, int head_dim, int kv_bits,
+                     float clip_lo, float clip_hi, int dtype, void* stream);
+int qat_qkv_prep_bwd(const void* dq_rot, const void* dk_rot, const void* dv_q, const uint8_t* k_mask,
+                     const uint8_t* v_mask, const float* cos_table, const float* sin_table,
+                     const int64_t* position_ids, void* dq, void* dk, void* dv, int64_t tokens, int heads,
+                     int head_dim, void* stream);
+
 /* Host-buffer convenience entry points (pinned or pageable host memory):
  * copy in, run, copy out on `stream`; `dev_scratch` must hold
  * qat_host_scratch_bytes(...) bytes of device memory. */

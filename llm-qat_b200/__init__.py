@@ -12,10 +12,12 @@ from __future__ import annotations
 
 import sys
 
-from . import _lib, utils_quant
+from . import _lib, fused_ops, model_patch, utils_quant
+from .model_patch import fuse_kd_loss, fuse_model, mark_causal_mask, unfuse_model
 from .utils_quant import AsymQuantizer, QuantizeLinear, SymQuantizer
 
-__all__ = ["SymQuantizer", "AsymQuantizer", "QuantizeLinear", "install", "utils_quant"]
+__all__ = ["SymQuantizer", "AsymQuantizer", "QuantizeLinear", "install", "utils_quant", "fused_ops",
+           "fuse_model", "unfuse_model", "fuse_kd_loss", "mark_causal_mask"]
 __version__ = "0.1.0"
 
 

@@ -58,6 +58,23 @@ def _declare(lib):
         "qat_attn_fwd": (I, [P, P, P, P, P, I, I, I, I, F, I, P]),
         # q, k, v, o, do, lse, delta, dq, dk, dv, B, S, H, D, scale, causal, stream
         "qat_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
+        # student, teacher, loss, row_kl, row_stat, rows, V, batch, dtype, stream
+        "qat_kd_loss_fwd": (I, [P, P, P, P, P, L, L, L, I, P]),
+        # student, teacher, row_stat, grad_loss, grad_student, rows, V, batch, dtype, stream
+        "qat_kd_loss_bwd": (I, [P, P, P, P, P, L, L, L, I, P]),
+        # x, w, y, rstd, codes, row_e, mask, lo, hi, rows, cols, eps, dtype, bits, stream
+        "qat_rmsnorm_feed_fwd": (I, [P, P, P, P, P, P, P, F, F, L, L, F, I, I, P]),
+        "qat_rmsnorm_bwd_workspace_bytes": (Z, [L, L]),
+        # gy, x, w, rstd, gx, gw, ws, ws_bytes, rows, cols, stream
+        "qat_rmsnorm_bwd": (I, [P, P, P, P, P, P, P, Z, L, L, P]),
+        # gate, up, act, codes, row_e, mask, lo, hi, rows, cols, dtype, bits, stream
+        "qat_swiglu_feed_fwd": (I, [P, P, P, P, P, P, F, F, L, L, I, I, P]),
+        # g, gate, up, d_gate, d_up, n, stream
+        "qat_swiglu_bwd": (I, [P, P, P, P, P, L, P]),
+        # q, k, v, qo, ko, vo, kmask, vmask, cos, sin, pos, tokens, heads, head_dim, kv_bits, lo, hi, dtype, stream
+        "qat_qkv_prep_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, F, F, I, P]),
+        # dq_rot, dk_rot, dv_q, kmask, vmask, cos, sin, pos, dq, dk, dv, tokens, heads, head_dim, stream
+        "qat_qkv_prep_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, I, P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
         "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),

@@ -349,6 +349,15 @@ def _feed_views(blob: torch.Tensor, rows: int, cols: int):
 _ACT_SLOT: dict = {}
 
 
+def register_activation_feed(y: torch.Tensor, blob: torch.Tensor, rows: int, cols: int, dt: int, bits: int) -> None:
+    """A producer kernel (fused_ops.rmsnorm / swiglu) already emitted the codes of ``y``: publish them in
+    the activation slot so the QuantizeLinear layers that receive this very tensor object reuse them
+     — same key a consumer would have stored after quantizing ``y`` itself."""
+    dev = y.device
+    key = (y.data_ptr(), y._version, rows, cols, dt, bits, _stream_ptr(dev))
+    _ACT_SLOT[dev.index] = (key, None, blob, weakref.ref(y))
+
+
 class _QuantLinearFn(torch.autograd.Function):
     """QuantizeLinear main path (3 <= w_bits <= 8, 3 <= a_bits <= 8, symmetric,
     per-row scales) on the integer grid — reference utils_quant.py:197-201,244-250.

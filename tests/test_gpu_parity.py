@@ -866,3 +866,170 @@ def test_config2_full_shape_vs_reference_chain():
         rel = ((outs[1] - outs[0]).norm() / outs[0].norm()).item()
         rows = ((outs[1] - outs[0]).norm(dim=1) / outs[0].norm(dim=1)).max().item()
         assert rel <= 1e-2 and rows <= 1e-2, (amp, rel, rows)
+
+
+# --------------------------------------------------------------- round 2: attention, KD loss, producers
+def _eager_attention(q, k, v, causal=True):
+    """modeling_llama_quant.py:352-377 on [B, S, H, D] inputs"""
+    import math
+
+    B, S, H, D = q.shape
+    qh, kh, vh = (t.transpose(1, 2) for t in (q, k, v))
+    w = torch.matmul(qh, kh.transpose(2, 3)) / math.sqrt(D)
+    if causal:
+        m = torch.full((S, S), torch.finfo(w.dtype).min, device=w.device, dtype=w.dtype).triu(1)
+        w = torch.max(w + m[None, None], torch.tensor(torch.finfo(w.dtype).min, device=w.device))
+    w = torch.softmax(w, dim=-1, dtype=torch.float32).to(qh.dtype)
+    return torch.matmul(w, vh).transpose(1, 2)
+
+
+@pytest.mark.parametrize("B,S,H,causal", [(1, 128, 1, True), (2, 320, 3, True), (1, 200, 2, True), (1, 72, 1, True),
+                                          (1, 512, 2, False), (1, 2048, 2, True)])
+def test_fused_attention_forward_backward_vs_reference_chain(B, S, H, causal):
+    """tcgen05 attention (fwd + bwd) vs the reference's eager chain in bf16 and an fp32 statement of it:
+    the fused kernel must be within 1e-2 of the fp32 result and at least as close to it as eager bf16."""
+    from llm_qat_b200.fused_ops import causal_attention
+
+    gen = torch.Generator().manual_seed(S + H)
+    mk = lambda: torch.randn(B, S, H, 128, generator=gen).bfloat16().cuda().requires_grad_(True)  # noqa: E731
+    q, k, v = mk(), mk(), mk()
+    go = torch.randn(B, S, H, 128, generator=gen).bfloat16().cuda()
+    o = causal_attention(q, k, v, causal=causal)
+    o.backward(go)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    of = _eager_attention(qf, kf, vf, causal)
+    of.backward(go.float())
+    q2, k2, v2 = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    oe = _eager_attention(q2, k2, v2, causal)
+    oe.backward(go)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    for name, mine, eager, exact in (("o", o, oe, of), ("dq", q.grad, q2.grad, qf.grad), ("dk", k.grad, k2.grad, kf.grad),
+                                     ("dv", v.grad, v2.grad, vf.grad)):
+        assert torch.isfinite(mine).all(), name
+        assert rel(mine, exact) <= 1e-2, (name, rel(mine, exact))
+        assert rel(mine, exact) <= 1.2 * rel(eager, exact) + 1e-4, (name, rel(mine, exact), rel(eager, exact))
+        assert rel(mine, eager) <= 1e-2, (name, rel(mine, eager))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 32000), (1, 33, 1000), (3, 5, 12)])
+def test_fused_kd_loss_matches_kd_trainer_formula(dtype, shape):
+    """utils/kd_trainer.py:42-48 — KL(batchmean) of log_softmax(student) vs softmax(teacher): loss to 1e-5
+    relative, gradient to 1e-4 of its norm (fp32 arithmetic in both; summation order differs)."""
+    from llm_qat_b200.fused_ops import kd_loss
+
+    gen = torch.Generator().manual_seed(7)
+    s0 = (torch.randn(*shape, generator=gen) * 3).to(dtype).cuda()
+    t0 = (torch.randn(*shape, generator=gen) * 3).to(dtype).cuda()
+    s1 = s0.clone().requires_grad_(True)
+    s2 = s0.clone().requires_grad_(True)
+    ref = torch.nn.functional.kl_div(torch.log_softmax(s1.float(), dim=2), torch.softmax(t0.float(), dim=2),
+                                     reduction="batchmean")
+    mine = kd_loss(s2, t0)
+    assert mine.dtype == torch.float32 and mine.dim() == 0
+    assert abs(mine.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7, (mine.item(), ref.item())
+    (ref * 0.5).backward()
+    (mine * 0.5).backward()
+    err = (s2.grad.float() - s1.grad.float()).norm() / s1.grad.float().norm()
+    assert err.item() <= (1e-4 if dtype == torch.float32 else 6e-3), err.item()
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_rmsnorm_and_swiglu_producers_emit_the_consumers_codes(amp):
+    """(f)-3: y / act equal the eager ops' bits (RMSNorm up to the summation order of mean(x^2)), and the
+    codes, divisors and STE mask emitted alongside are exactly what qat_sym_fwd's feed gives for them."""
+    from llm_qat_b200 import fused_ops as FO
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.utils_quant import _ACT_SLOT, _feed_views, fake_quant_forward
+
+    gen = torch.Generator().manual_seed(31)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        for C, T in ((4096, 300), (5120, 17), (1000, 64)):
+            x = (torch.randn(T, C, generator=gen) * 2).bfloat16().cuda()
+            w = (1 + 0.1 * torch.randn(C, generator=gen)).bfloat16().cuda()
+            y = FO.rmsnorm(x, w, 1e-6, feed_bits=8)
+            var = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+            y_ref = w * (x * torch.rsqrt(var + 1e-6)).to(torch.bfloat16)
+            assert (y != y_ref).float().mean().item() < 2e-3          # <= 1 bf16 ulp where rstd differs by 1 ulp
+            assert ((y.float() - y_ref.float()).abs() <= 0.01 * y_ref.float().abs() + 1e-6).all()
+            codes, e, mask = _feed_views(_ACT_SLOT[0][2], T, C)
+            _, c8, _, e_ref, m_ref = fake_quant_forward(y, 8, False, True, want_y=False, codes_kind=CODES_I8,
+                                                        want_scales=True, mask_clip=(-2.0, 2.0), amp=amp)
+            assert torch.equal(codes, c8) and torch.equal(e, e_ref) and torch.equal(mask, m_ref)
+        for C, T in ((11008, 100), (13824, 9), (2000, 33)):
+            gate = (torch.randn(T, C, generator=gen) * 2).bfloat16().cuda()
+            up = torch.randn(T, C, generator=gen).bfloat16().cuda()
+            act = FO.swiglu(gate, up, feed_bits=8)
+            ref = torch.nn.functional.silu(gate) * up
+            assert (act != ref).float().mean().item() < 2e-2          # __expf vs expf: rare 1-ulp differences
+            assert ((act.float() - ref.float()).abs() <= 0.01 * ref.float().abs() + 1e-6).all()
+            codes, e, mask = _feed_views(_ACT_SLOT[0][2], T, C)
+            _, c8, _, e_ref, m_ref = fake_quant_forward(act, 8, False, True, want_y=False, codes_kind=CODES_I8,
+                                                        want_scales=True, mask_clip=(-2.0, 2.0), amp=amp)
+            assert torch.equal(codes, c8) and torch.equal(e, e_ref) and torch.equal(mask, m_ref)
+
+
+def test_producer_backward_kernels_vs_autograd():
+    from llm_qat_b200 import fused_ops as FO
+
+    gen = torch.Generator().manual_seed(37)
+    T, C = 200, 1024
+    x0 = torch.randn(T, C, generator=gen).bfloat16().cuda()
+    w0 = (1 + 0.1 * torch.randn(C, generator=gen)).bfloat16().cuda()
+    g0 = torch.randn(T, C, generator=gen).bfloat16().cuda()
+    x1, w1 = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    FO.rmsnorm(x1, w1, 1e-6).backward(g0)
+    x2, w2 = x0.float().requires_grad_(True), w0.float().requires_grad_(True)
+    var = x2.pow(2).mean(-1, keepdim=True)
+    (w2 * (x2 * torch.rsqrt(var + 1e-6))).backward(g0.float())
+    rel = lambda a, b: ((a.float() - b).norm() / b.norm()).item()  # noqa: E731
+    assert rel(x1.grad, x2.grad) <= 6e-3 and rel(w1.grad, w2.grad) <= 6e-3, (rel(x1.grad, x2.grad), rel(w1.grad, w2.grad))
+    a0 = torch.randn(T, C, generator=gen).bfloat16().cuda()
+    u0 = torch.randn(T, C, generator=gen).bfloat16().cuda()
+    a1, u1 = a0.clone().requires_grad_(True), u0.clone().requires_grad_(True)
+    FO.swiglu(a1, u1).backward(g0)
+    a2, u2 = a0.float().requires_grad_(True), u0.float().requires_grad_(True)
+    (torch.nn.functional.silu(a2) * u2).backward(g0.float())
+    assert rel(a1.grad, a2.grad) <= 8e-3 and rel(u1.grad, u2.grad) <= 8e-3, (rel(a1.grad, a2.grad), rel(u1.grad, u2.grad))
+
+
+@pytest.mark.parametrize("amp", [False, True])
+@pytest.mark.parametrize("kv_bits", [4, 8, 32])
+def test_qkv_prep_equals_kv_fake_quant_then_rope(amp, kv_bits):
+    """One launch == SymQuantizer.apply on K and V (bit-exact values: V is compared directly) followed by
+    apply_rotary_pos_emb (modeling_llama_quant.py:320-341), forward and backward, vs the eager chain."""
+    from harness import llama_qat as H
+    from llm_qat_b200 import SymQuantizer
+    from llm_qat_b200.fused_ops import qkv_prep
+
+    B, S, nh = 2, 96, 3
+    gen = torch.Generator().manual_seed(41)
+    mk = lambda: (torch.randn(B, S, nh * 128, generator=gen) * 1.5).bfloat16().cuda()  # noqa: E731
+    q0, k0, v0 = mk(), mk(), mk()
+    gq, gk, gv = mk(), mk(), mk()
+    rot = H.RotaryEmbedding(128, 256).cuda()
+    pos = torch.arange(S, device="cuda")[None].expand(B, S)
+    cos_t, sin_t = rot.cos_cached[0, 0].contiguous(), rot.sin_cached[0, 0].contiguous()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        q1, k1, v1 = (t.clone().requires_grad_(True) for t in (q0, k0, v0))
+        qr, kr, vq = qkv_prep(q1, k1, v1, cos_t, sin_t, pos, nh, kv_bits)
+        torch.autograd.backward((qr, kr, vq), (gq, gk, gv))
+        q2, k2, v2 = (t.clone().requires_grad_(True) for t in (q0, k0, v0))
+        kq, vq2 = k2, v2
+        if kv_bits < 32:
+            kq = SymQuantizer.apply(k2, CLIP, kv_bits, False)
+            vq2 = SymQuantizer.apply(v2, CLIP, kv_bits, False)
+        sh = (B, S, nh, 128)
+        qh, kh, vh = q2.view(sh).transpose(1, 2), kq.view(sh).transpose(1, 2), vq2.view(sh).transpose(1, 2)
+        cos, sin = rot(vh, seq_len=S)
+        qe, ke = H._apply_rotary_pos_emb(qh, kh, cos, sin, pos)
+        qe, ke = (t.transpose(1, 2).reshape(B, S, nh * 128) for t in (qe, ke))
+        torch.autograd.backward((qe, ke, vq2), (gq.to(qe.dtype), gk.to(ke.dtype), gv.to(vq2.dtype)))
+    assert torch.equal(vq, vq2.to(torch.bfloat16))
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()  # noqa: E731
+    assert rel(qr, qe) <= 4e-3 and rel(kr, ke) <= 4e-3, (rel(qr, qe), rel(kr, ke))
+    if not amp:
+        assert torch.equal(qr, qe) and torch.equal(kr, ke)     # plain bf16: every op rounded like eager
+    assert torch.equal(v1.grad, v2.grad)
+    assert rel(q1.grad, q2.grad) <= 6e-3 and rel(k1.grad, k2.grad) <= 6e-3, (rel(q1.grad, q2.grad), rel(k1.grad, k2.grad))
+    assert bool(((k1.grad == 0) == (k2.grad == 0)).float().mean() > 0.999)

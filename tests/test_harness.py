@@ -300,3 +300,147 @@ def test_training_trajectory_matches_the_reference_chain(autocast, monkeypatch):
     assert unfused == ref, [(i, a, b) for i, (a, b) in enumerate(zip(unfused, ref)) if a != b][:3]
     rel = max(abs(a - b) / abs(b) for a, b in zip(fused, ref))
     assert rel < 0.15 and abs(fused[-1] - ref[-1]) / ref[-1] < 0.15, (rel, fused[-3:], ref[-3:])
+
+
+# --------------------------------------------------------------------------- round 2: fuse_model
+@needs_reference
+def test_fuse_model_binds_the_unmodified_reference_model():
+    """llm_qat_b200.fuse_model on a LLaMA built from the UNMODIFIED reference model file: attention, MLP,
+    RMSNorm and the model's mask builder are rebound on the instances (classes, parameters and state dict
+    untouched), the causal mask the reference builds (:599-629) is recognised, a padded one is not, and
+    unfuse_model restores everything.  (No product forward here: no CPU path.)"""
+    import subprocess
+
+    code = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, %r)
+import torch
+import llm_qat_b200
+import models
+llm_qat_b200.install()
+from models.configuration_llama import LlamaConfig
+from models import modeling_llama_quant as M
+from llm_qat_b200 import model_patch as MP
+cfg = LlamaConfig(hidden_size=256, intermediate_size=688, num_attention_heads=2, num_hidden_layers=2, vocab_size=128,
+                  max_position_embeddings=64, w_bits=4, a_bits=8, kv_bits=4)
+cfg.kv_bits = 4
+model = M.LlamaForCausalLM(cfg)
+keys = sorted(model.state_dict().keys())
+cls_fwd = M.LlamaAttention.forward
+llm_qat_b200.fuse_model(model)
+llm_qat_b200.fuse_model(model)                       # idempotent
+lay = model.model.layers[0]
+assert lay.self_attn.forward.__func__ is MP._attention_forward and lay.self_attn.head_dim == 128
+assert lay.mlp.forward.__func__ is MP._mlp_forward and lay.mlp._qat_feed_bits == 8
+assert lay.input_layernorm.forward.__func__ is MP._rmsnorm_forward and lay.input_layernorm._qat_feed_bits == 8
+assert model.model.norm.forward.__func__ is MP._rmsnorm_forward and model.model.norm._qat_feed_bits == 0
+assert model.model.forward.__func__ is MP._model_forward
+assert M.LlamaAttention.forward is cls_fwd and sorted(model.state_dict().keys()) == keys
+# the mask the reference builds for "no attention_mask" is registered as causal ...
+emb = torch.zeros(1, 8, 256)
+model.model._qat_plain_causal = True
+m = model.model._prepare_decoder_attention_mask(torch.ones(1, 8, dtype=torch.bool), (1, 8), emb, 0)
+assert MP._is_causal(m) and m.shape == (1, 1, 8, 8)
+assert MP._is_causal(m.detach().view(m.shape))        # same storage (what a checkpoint re-wrap passes on)
+assert not MP._is_causal(m.clone())
+# ... a padded one is not
+model.model._qat_plain_causal = False
+m2 = model.model._prepare_decoder_attention_mask(torch.tensor([[0, 1, 1, 1, 1, 1, 1, 1]]).bool(), (1, 8), emb, 0)
+assert not MP._is_causal(m2) and not MP._is_causal(m)
+# a CPU call falls through to the reference's own forward code path selection (non-CUDA -> original)
+assert lay.self_attn._qat_orig_forward.__func__ is cls_fwd
+llm_qat_b200.unfuse_model(model)
+assert "forward" not in lay.self_attn.__dict__ and "forward" not in model.model.__dict__
+assert lay.self_attn.forward.__func__ is cls_fwd
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr[-3000:]
+
+
+def _layer_pair(cfg, seed=0):
+    import llm_qat_b200
+
+    torch.manual_seed(seed)
+    ref = H.DecoderLayer(cfg, R).bfloat16().cuda()
+    new = H.DecoderLayer(cfg, llm_qat_b200.utils_quant).bfloat16().cuda()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 2:
+                p.normal_(0.0, 0.02)
+            else:
+                p.uniform_(0.5, 1.5)
+    new.load_state_dict(ref.state_dict())
+    llm_qat_b200.fuse_model(new)
+    return ref, new
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("autocast", [False, True])
+def test_fused_decoder_layer_matches_reference_chain(autocast):
+    """(f)-3/(f)-4 at the layer level: a decoder layer on the product with fuse_model (RMSNorm+feed,
+    qkv_prep, tcgen05 attention, SwiGLU+feed, own dgrad/wgrad) against the same layer on the reference's
+    eager chain; forward and every gradient within bf16 tolerance of it, measured against what the
+    integer-grid statement of the same layer (oracle.grid_module) deviates by."""
+    cfg = H.QatConfig(hidden_size=512, intermediate_size=1376, num_attention_heads=4, num_hidden_layers=1,
+                      max_position_embeddings=256, w_bits=4, a_bits=8, kv_bits=8)
+    ref, new = _layer_pair(cfg)
+    import llm_qat_b200
+
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(2, 256, 512, generator=g).bfloat16().cuda()
+    go = torch.randn(2, 256, 512, generator=g).bfloat16().cuda()
+    mask = H.causal_mask(2, 256, torch.bfloat16, "cuda")
+    pos = torch.arange(256, device="cuda")[None].expand(2, 256)
+    outs = []
+    for layer in (ref, new):
+        if layer is new:
+            llm_qat_b200.mark_causal_mask(mask)
+        x = x0.clone().requires_grad_(True)
+        n0 = llm_qat_b200._lib.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = layer(x, mask, pos)
+        y.backward(go)
+        grads = {n: p.grad.float() for n, p in layer.named_parameters()}
+        outs.append((y.float(), x.grad.float(), grads, llm_qat_b200._lib.launch_count() - n0))
+    (y_r, gx_r, gr_r, _), (y, gx, gr, launches) = outs
+    rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-30)).item()  # noqa: E731
+    assert rel(y, y_r) <= 1e-2, rel(y, y_r)
+    assert rel(gx, gx_r) <= 3e-2, rel(gx, gx_r)
+    for n in gr_r:
+        assert rel(gr[n], gr_r[n]) <= 3e-2, (n, rel(gr[n], gr_r[n]))
+    assert launches >= 30, launches     # the layer really ran on this library's kernels
+
+
+@pytest.mark.gpu
+def test_fused_model_training_trajectory_tracks_the_reference_chain():
+    """30 QAT steps with fuse_model + the fused KD loss against the reference chain (same init, data):
+    the loss goes down and tracks the reference's trajectory."""
+    import llm_qat_b200
+
+    cfg = H.QatConfig(hidden_size=256, intermediate_size=688, num_attention_heads=2, num_hidden_layers=2,
+                      vocab_size=512, max_position_embeddings=128, w_bits=4, a_bits=8, kv_bits=4)
+
+    def run(quant, fused):
+        torch.manual_seed(0)
+        student = H.CausalLM(cfg, quant, fused=fused).bfloat16().cuda()
+        teacher = H.build_teacher(cfg, fused=fused).bfloat16().cuda()
+        teacher.load_state_dict(student.state_dict())
+        with torch.no_grad():
+            for p in student.parameters():
+                p.add_(torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())).to(p).mul_(0.01))
+        opt = torch.optim.AdamW(student.parameters(), lr=1e-3)
+        g = torch.Generator().manual_seed(99)
+        losses = []
+        for _ in range(30):
+            ids = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).cuda()
+            losses.append(float(H.qat_step(student.train(), teacher, ids, opt, autocast=True,
+                                           loss_fn=llm_qat_b200.fused_ops.kd_loss if fused else None)))
+        return losses
+
+    ref = run(R, False)
+    fused = run(llm_qat_b200.utils_quant, True)
+    assert all(np.isfinite(fused)) and fused[-1] < fused[0]
+    rel = max(abs(a - b) / abs(b) for a, b in zip(fused, ref))
+    assert rel < 0.15 and abs(fused[-1] - ref[-1]) / ref[-1] < 0.15, (rel, fused[-3:], ref[-3:])
