@@ -28,10 +28,15 @@ def _timed(fn, warmup, steps):
 
 
 def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, device="cuda", seed=1234,
-               autocast=False):
-    """Config 3: one LlamaDecoderLayer W4A8KV4 bf16, hidden_states [bsz, seq, H], fwd + bwd."""
+               autocast=False, fused=False):
+    """Config 3: one LlamaDecoderLayer W4A8KV4 bf16, hidden_states [bsz, seq, H], fwd + bwd.
+    ``fused``: llm_qat_b200.fuse_model on the layer (attention / MLP / RMSNorm kernels)."""
     torch.manual_seed(0)
     layer = H.DecoderLayer(cfg, quant).bfloat16().to(device)
+    if fused:
+        import llm_qat_b200
+
+        llm_qat_b200.fuse_model(layer)
     with torch.no_grad():
         for p in layer.parameters():
             if p.dim() == 2:
@@ -40,6 +45,8 @@ def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, dev
     x = torch.randn(bsz, seq, cfg.hidden_size, generator=g).bfloat16().to(device).requires_grad_(True)
     go = torch.randn(bsz, seq, cfg.hidden_size, generator=g).bfloat16().to(device)
     mask = H.causal_mask(bsz, seq, torch.bfloat16, device)
+    if fused:
+        llm_qat_b200.mark_causal_mask(mask)
     pos = torch.arange(seq, device=device)[None].expand(bsz, seq)
 
     def step():
@@ -53,31 +60,38 @@ def time_layer(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, dev
     t = _timed(step, warmup, steps)
     ms = statistics.median(t)
     return {"ms_fwd_bwd": round(ms, 3), "tokens_per_s": round(bsz * seq / ms * 1e3), "seq": seq, "bsz": bsz,
-            "autocast": autocast}
+            "autocast": autocast, "fused_model": fused}
 
 
 def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, device="cuda", rank=0, world=1,
-                  lr=2e-5, autocast=False):
+                  lr=2e-5, autocast=False, fused=False, bucket_cap_mb=None):
     """Config 4/5: student (quantized) + frozen FP teacher of identical init, KD loss,
     gradient checkpointing, AdamW; DDP (NCCL all-reduce of the gradients) when world > 1.
     Returns this rank's median step time; the caller reduces max over ranks."""
     torch.manual_seed(0)
     with torch.device(device):
-        student = H.CausalLM(cfg, quant).bfloat16()
-        teacher = H.build_teacher(cfg).bfloat16()
+        student = H.CausalLM(cfg, quant, fused=fused).bfloat16()
+        teacher = H.build_teacher(cfg, fused=fused).bfloat16()
     teacher.load_state_dict(student.state_dict())
     student.train()
     model = student
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
 
-        model = DDP(student, device_ids=[torch.device(device).index], gradient_as_bucket_view=True)
+        kw = {} if bucket_cap_mb is None else {"bucket_cap_mb": bucket_cap_mb}
+        model = DDP(student, device_ids=[torch.device(device).index], gradient_as_bucket_view=True, **kw)
     opt = torch.optim.AdamW(student.parameters(), lr=lr)
     g = torch.Generator().manual_seed(1234 + rank)
     ids = torch.randint(0, cfg.vocab_size, (bsz, seq), generator=g).to(device)
 
+    loss_fn = None
+    if fused:
+        import llm_qat_b200
+
+        loss_fn = llm_qat_b200.fused_ops.kd_loss
+
     def step():
-        H.qat_step(model, teacher, ids, opt, autocast=autocast)
+        H.qat_step(model, teacher, ids, opt, autocast=autocast, loss_fn=loss_fn)
 
     t = _timed(step, warmup, steps)
     ms = statistics.median(t)
@@ -85,4 +99,5 @@ def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, 
     del opt, model, student, teacher
     torch.cuda.empty_cache()
     return {"ms_per_step": round(ms, 2), "tokens_per_s_per_gpu": round(bsz * seq / ms * 1e3), "seq": seq,
-            "bsz_per_gpu": bsz, "peak_mem_GiB": round(mem, 1), "layers": cfg.num_hidden_layers, "autocast": autocast}
+            "bsz_per_gpu": bsz, "peak_mem_GiB": round(mem, 1), "layers": cfg.num_hidden_layers, "autocast": autocast,
+            "fused_model": fused}

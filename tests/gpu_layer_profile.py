@@ -18,12 +18,20 @@ cfg = H.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4)
 seq, bsz = 2048, 1
 AUTOCAST = len(sys.argv) > 1 and sys.argv[1] == "autocast"   # the recipe's context (kd_trainer.py:106)
 import contextlib
-for name, quant in (("b200_fused", llm_qat_b200.utils_quant), ("reference_eager", R)):
+ONLY = [a for a in sys.argv[1:] if a != "autocast"]
+for name, quant in (("b200_fused_model", llm_qat_b200.utils_quant), ("b200_fused", llm_qat_b200.utils_quant),
+                    ("reference_eager", R)):
+    if ONLY and name not in ONLY:
+        continue
     torch.manual_seed(0)
     layer = H.DecoderLayer(cfg, quant).bfloat16().cuda()
+    if name == "b200_fused_model":
+        llm_qat_b200.fuse_model(layer)
     x = torch.randn(bsz, seq, cfg.hidden_size).bfloat16().cuda().requires_grad_(True)
     go = torch.randn(bsz, seq, cfg.hidden_size).bfloat16().cuda()
     mask = H.causal_mask(bsz, seq, torch.bfloat16, "cuda")
+    if name == "b200_fused_model":
+        llm_qat_b200.mark_causal_mask(mask)
     pos = torch.arange(seq, device="cuda")[None].expand(bsz, seq)
     def step():
         with (torch.autocast("cuda", dtype=torch.bfloat16) if AUTOCAST else contextlib.nullcontext()):
@@ -45,8 +53,9 @@ for name, quant in (("b200_fused", llm_qat_b200.utils_quant), ("reference_eager"
     ka = [e for e in prof.key_averages() if getattr(e, "device_type", None) is not None
           and "CUDA" in str(e.device_type) and getattr(e, "self_device_time_total", 0) > 0]
     tot = sum(e.self_device_time_total for e in ka)
-    ours = sum(e.self_device_time_total for e in ka if "qat::" in e.key)
-    gemm = sum(e.self_device_time_total for e in ka if "nvjet" in e.key or "gemm" in e.key.lower() or "cutlass" in e.key.lower())
+    ours = sum(e.self_device_time_total for e in ka if "qat::" in e.key or "qat" in e.key.split("(")[0])
+    gemm = sum(e.self_device_time_total for e in ka if "qat::" not in e.key and
+               ("nvjet" in e.key or "gemm" in e.key.lower() or "cutlass" in e.key.lower()))
     print(f"device kernel time per step: {tot/3/1e3:.3f} ms = libqat_b200 {ours/3/1e3:.3f} + library GEMM {gemm/3/1e3:.3f} "
           f"+ ATen (attention, norms, residuals, copies) {(tot-ours-gemm)/3/1e3:.3f}; {sum(e.count for e in ka)//3} launches")
     for e in sorted(ka, key=lambda e: -e.self_device_time_total)[:45]:
