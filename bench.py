@@ -42,6 +42,14 @@ WORKLOAD = ("configs[1]: QuantizeLinear up_proj operands, x bf16[8192,4096] A8 p
             "W bf16[11008,4096] W4 per-channel, SymQuantizer fwd + STE bwd")
 
 
+def bench_config(world: int):
+    """The `config` object — identical in the b200 and the reference arm (same workload, same partitioning)."""
+    return {"workload": WORKLOAD, "bytes_per_step_per_gpu": STEP_BYTES,
+            "l2": "inputs larger than L2 (x+W = 157 MB per step, 786 MB touched between re-reads)",
+            "parallelism": f"dp{world}: every rank fake-quantizes its own 8192-token batch and weight replica; "
+                           "rows are independent, no data-path collective"}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
 # `ncu --set full` capture (profiles/): filled in from profiles/r01_ncu_summary.json
 def _load_ncu_traffic():
@@ -192,32 +200,59 @@ class Step:
             self.launch(i, stream)
 
 
-def time_config1_fp32(device, steps):
-    """BASELINE configs[0] shapes on the GPU: fp32 [8192,4096], fwd+bwd per quantizer."""
+def time_config1_fp32(device, steps, pk):
+    """BASELINE configs[0] on the GPU: fp32 [8192, 4096], SymQuantizer (W4 per-channel, A8 per-token) and
+    AsymQuantizer (A8, A4), forward + STE backward, each kernel with its own roofline object (algorithmic
+    bytes: fwd 2e, bwd 3e per element, e = 4).  Two buffer sets alternate so that no launch
+    re-reads what the previous one left in L2 (134 MB per tensor, 4 tensors per set)."""
     from llm_qat_b200 import _lib
 
     L = _lib.lib()
     g = torch.Generator().manual_seed(1234)
-    x = (torch.randn(8192, 4096, generator=g) * 0.5).to(device)
-    gr = torch.randn(8192, 4096, generator=g).to(device)
-    y, dx = torch.empty_like(x), torch.empty_like(x)
+    sets = []
+    for _ in range(2):
+        x = (torch.randn(8192, 4096, generator=g) * 0.5).to(device)
+        gr = torch.randn(8192, 4096, generator=g).to(device)
+        sets.append((x, gr, torch.empty_like(x), torch.empty_like(x)))
+    n = 8192 * 4096
     st = torch.cuda.current_stream().cuda_stream
     out = {}
-    for name, fn, bits in (("sym_w4", L.qat_sym_fwd, 4), ("sym_a8", L.qat_sym_fwd, 8),
-                           ("asym_a8", L.qat_asym_fwd, 8), ("asym_a4", L.qat_asym_fwd, 4)):
-        def once():
-            _lib.check(fn(x.data_ptr(), y.data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, 8192, 4096, 0, bits, 0, 0, st))
-            _lib.check(L.qat_ste_bwd(gr.data_ptr(), x.data_ptr(), dx.data_ptr(), 0, -2.0, 2.0, x.numel(), 0, st))
-        for _ in range(3):
-            once()
+
+    def timed(fn):
+        for i in range(4):
+            fn(i)
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            once()
+        for i in range(steps):
+            fn(i)
         e1.record()
         e1.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        out[name] = {"ms_fwd_bwd": round(ms, 4), "GBps": round(x.numel() * 20 / ms / 1e6, 1)}
+        return e0.elapsed_time(e1) / steps
+
+    for name, fn, bits in (("sym_w4", L.qat_sym_fwd, 4), ("sym_a8", L.qat_sym_fwd, 8),
+                           ("asym_a8", L.qat_asym_fwd, 8), ("asym_a4", L.qat_asym_fwd, 4)):
+        def fwd(i):
+            x, gr, y, dx = sets[i & 1]
+            _lib.check(fn(x.data_ptr(), y.data_ptr(), 0, 0, 0, 0, 0, 0.0, 0.0, 8192, 4096, 0, bits, 0, 0, st))
+
+        def bwd(i):
+            x, gr, y, dx = sets[i & 1]
+            _lib.check(L.qat_ste_bwd(gr.data_ptr(), x.data_ptr(), dx.data_ptr(), 0, -2.0, 2.0, n, 0, st))
+
+        def both(i):
+            fwd(i)
+            bwd(i)
+        ms_f, ms_b, ms = timed(fwd), timed(bwd), timed(both)
+
+        def roof(bytes_, ms_):
+            a = bytes_ / ms_ / 1e6
+            return {"bound": "hbm", "achieved": round(a, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(a / pk["hbm_gbs"], 4), "bytes_per_launch": bytes_, "us_per_launch": round(ms_ * 1e3, 2)}
+        out[name] = {"ms_fwd_bwd": round(ms, 4), "GBps": round(n * 20 / ms / 1e6, 1),
+                     "frac_of_hbm_peak": round(n * 20 / ms / 1e6 / pk["hbm_gbs"], 4),
+                     "roofline_fwd": roof(n * 8, ms_f), "roofline_bwd": roof(n * 12, ms_b)}
+    out["workload"] = "configs[0]: fp32 [8192, 4096], Sym W4 / A8 and Asym A8 / A4, fwd + STE bwd (20 B/elem)"
     return out
 
 
@@ -387,18 +422,106 @@ def time_qlinear(device, x, w, steps, pk):
         e1.synchronize()
         ms = e0.elapsed_time(e1) / steps
         res[name] = {"ms": round(ms, 4), "TOPs": round(flop / ms / 1e9, 1), "tokens_per_s": round(T_TOK / ms * 1e3)}
-    # tcgen05 kind::i8 retires 2x the MACs of kind::f16 per SM cycle (nominal 4.5 vs 2.25 P), so the
-    # tensor roofline of this kernel is twice the measured cuBLAS bf16 figure; the fraction of the
-    # plain bf16 peak is kept beside it, and the ncu tensor-pipe-active share from profiles/.
-    peak_i8 = 2.0 * pk["bf16_tflops"]
+    # comparators, measured in this run at the same shape:
+    #  (1) the library int8 GEMM (torch._int_mm -> cuBLASLt, int32 output): the measured int8 tensor peak
+    #      this kernel's roofline fraction is taken against;
+    #  (2) the reference's own QuantizeLinear.forward, eager on this GPU (oracle/ref_module: 18 elementwise
+    #      kernels + a cuBLAS bf16 GEMM on dequantized operands, utils_quant.py:190-254).
+    lib_tops = None
+    try:
+        b_t = qw.t().contiguous()     # [K, N]; _int_mm wants a row-major second operand
+        torch._int_mm(qx, b_t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            torch._int_mm(qx, b_t)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        lib_tops = flop / ms / 1e9
+        res["library_int8_gemm"] = {"ms": round(ms, 4), "TOPs": round(lib_tops, 1),
+                                    "what": "torch._int_mm (cuBLASLt int8, s32 out) 8192x11008x4096"}
+        del b_t
+    except Exception as e:  # noqa: BLE001
+        res["library_int8_gemm"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        from oracle import ref_module
+
+        lin = ref_module.QuantizeLinear(K_IN, N_OUT, w_bits=W_BITS, a_bits=A_BITS).bfloat16().to(device)
+        with torch.no_grad():
+            lin.weight.copy_(w)
+            for _ in range(2):
+                lin(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n_ref = max(3, steps // 2)
+            for _ in range(n_ref):
+                lin(x)
+            e1.record()
+            e1.synchronize()
+        ms = e0.elapsed_time(e1) / n_ref
+        res["reference_eager"] = {"ms": round(ms, 4), "tokens_per_s": round(T_TOK / ms * 1e3),
+                                  "what": "reference QuantizeLinear.forward op chain, eager on this GPU (bf16)",
+                                  "speedup_of_forward": round(ms / res["forward"]["ms"], 2)}
+        del lin
+    except Exception as e:  # noqa: BLE001
+        res["reference_eager"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    # tensor roofline: the measured library int8 GEMM when available (else twice the measured cuBLAS bf16
+    # figure: kind::i8 retires 2x the MACs of kind::f16 per SM cycle), with the bf16 fraction beside it
+    peak_i8 = lib_tops if lib_tops else 2.0 * pk["bf16_tflops"]
     res["roofline"] = {"bound": "tensor", "achieved": res["gemm"]["TOPs"], "peak": round(peak_i8, 1),
                        "unit": "TOP/s", "frac": round(res["gemm"]["TOPs"] / peak_i8, 4),
+                       "frac_of_2x_bf16_peak": round(res["gemm"]["TOPs"] / (2.0 * pk["bf16_tflops"]), 4),
                        "frac_of_bf16_peak": round(res["gemm"]["TOPs"] / pk["bf16_tflops"], 4),
-                       "peak_source": "2 x bf16_tflops of " + pk["source"] + " (int8 MMA: twice the bf16 MAC rate)",
+                       "peak_source": ("measured in this run: torch._int_mm (cuBLASLt int8) at the same shape" if lib_tops
+                                       else "2 x bf16_tflops of " + pk["source"]),
                        "tensor_pipe_active_ncu": NCU_GEMM.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                        "traffic": NCU_GEMM.get("dram_bytes_per_launch"),
                        "kernel": "qlinear_i8_kernel<bf16, cta_group 2> 8192x11008x4096"}
     return res
+
+
+def link_probe(device, h_src, h_dst, barrier, dist, reps=5):
+    """Pinned-host copies only, every rank concurrently: STEP-sized H2D and D2H streams at once.
+    Returns per-direction GB/s of this rank (max-over-ranks time) and the aggregate over ranks."""
+    world = dist.get_world_size() if dist is not None else 1
+    nbytes = ELEMS * 2 * 2                    # what one e2e step moves each way
+    n_el = nbytes // h_src.element_size()
+    reps_src = [h_src.view(-1)] * ((n_el + h_src.numel() - 1) // h_src.numel())
+    d_in = torch.empty(h_src.numel(), dtype=h_src.dtype, device=device)
+    d_out = torch.empty(h_dst.numel(), dtype=h_dst.dtype, device=device)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    chunks = len(reps_src)
+
+    def run(n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s1.wait_stream(torch.cuda.current_stream())
+        s2.wait_stream(torch.cuda.current_stream())
+        for _ in range(n * chunks):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_src.view(-1), non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_dst.view(-1).copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n
+
+    run(1)
+    ms = run(reps)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    moved = chunks * h_src.numel() * h_src.element_size()
+    return {"ms_per_step_equivalent": round(ms * nbytes / moved, 3), "GBps_per_direction_per_gpu": round(moved / ms / 1e6, 1),
+            "GBps_per_direction_aggregate": round(world * moved / ms / 1e6, 1), "ranks_concurrent": world,
+            "what": "pinned H2D + D2H concurrently on every rank, no kernels: the ceiling of e2e on this host"}
 
 
 def run_b200(args):
@@ -538,6 +661,13 @@ def run_b200(args):
            "ms_per_step": round(e2e_ms / Ke, 3), "wall_ms_per_step": round(wall_ms / Ke, 3),
            "api": "llm_qat_b200.host_api.fake_quant_fwd_bwd_host -> qat_sym_fwd_bwd_host (pinned host buffers)"}
 
+    # the host link's own ceiling with all ranks busy at once (plain pinned H2D + D2H of the same byte
+    # counts, both directions concurrently): what the e2e figure is bounded by on this box
+    try:
+        e2e["link_probe"] = link_probe(device, hx, yx, barrier, dist)
+    except Exception as e:  # noqa: BLE001
+        e2e["link_probe"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     extras = {}
     if rank == 0:
         try:
@@ -545,7 +675,7 @@ def run_b200(args):
         except Exception as e:
             extras["qlinear"] = {"error": f"{type(e).__name__}: {e}"}
         try:
-            extras["config1_fp32"] = time_config1_fp32(device, max(3, min(K, 20)))
+            extras["config1_fp32"] = time_config1_fp32(device, max(4, min(K, 20)), pk)
         except Exception as e:
             extras["config1_fp32"] = {"error": f"{type(e).__name__}: {e}"}
         if args.shape_sweep:
@@ -553,12 +683,15 @@ def run_b200(args):
                 extras["shape_sweep"] = time_shape_sweep(device, max(3, min(K, 20)), pk)
             except Exception as e:
                 extras["shape_sweep"] = {"error": f"{type(e).__name__}: {e}"}
-    # ---- BASELINE config 4: full LLaMA-7B W4A8KV4 QAT step with KD loss, data-parallel
-    qat = None
+    # ---- BASELINE configs[2] (decoder layer) and configs[3] / [4] (full QAT step, data-parallel), with the
+    # comparator the north star names — the reference's eager-PyTorch GPU path (oracle/ref_module under the
+    # same harness, same N, same autocast context) — measured in the same run.
+    layer, qat = None, None
     if not args.no_qat_step:
         try:
             from harness import llama_qat as HQ
             from harness import qat_bench as QB
+            from oracle import ref_module as RM
 
             if args.qat_model == "13b":   # BASELINE configs[4]: LLaMA-13B W4A8KV8 (180 GB/GPU sizing: DESIGN.md section 6)
                 cfg7 = HQ.QatConfig.llama_13b(w_bits=4, a_bits=8, kv_bits=8)
@@ -568,19 +701,47 @@ def run_b200(args):
                 cfg7 = HQ.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4, num_hidden_layers=args.qat_layers)
             del step, x, w, gx, gw
             torch.cuda.empty_cache()
-            torch.cuda.reset_peak_memory_stats()
-            r = QB.time_qat_step(llm_qat_b200.utils_quant, cfg7, seq=2048, bsz=1, warmup=3,
-                                 steps=max(3, min(K, 10)), device=device, rank=rank, world=world,
-                                 autocast=True)   # the recipe: HF's Trainer runs the step in autocast(bf16)
-            ms = r["ms_per_step"]
-            if dist is not None:
+            nst = max(3, min(K, 10))
+
+            def reduce_max(ms):
+                if dist is None:
+                    return ms
                 t = torch.tensor([ms], device=device)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            qat = dict(r, ms_per_step=round(ms, 2), tokens_per_s=round(world * 2048 / ms * 1e3), n_gpus=world,
-                       model=("LLaMA-13B dims, random init, student W4A8KV8" if args.qat_model == "13b" else
-                              "LLaMA-7B dims, random init, student W4A8KV4") + " + frozen FP teacher, KD (KL batchmean), "
-                             "grad checkpointing, AdamW, bf16 inside torch.autocast(bf16) as kd_trainer.py:106 does" + (", DDP/NCCL all-reduce" if world > 1 else ""))
+                return float(t.item())
+
+            if rank == 0:   # configs[2]: one decoder layer fwd+bwd, seq 2048, inside autocast(bf16)
+                layer = {"workload": "configs[2]: LlamaDecoderLayer W4A8KV4 bf16, hidden_states [1, 2048, 4096], fwd + bwd, "
+                                     "inside torch.autocast(bf16)"}
+                for name, quant, fm in (("b200_fused_model", llm_qat_b200.utils_quant, True),
+                                        ("b200_quant_path_only", llm_qat_b200.utils_quant, False),
+                                        ("reference_eager_gpu", RM, False)):
+                    layer[name] = QB.time_layer(quant, cfg7, warmup=3, steps=nst, device=device, autocast=True, fused=fm)
+                layer["speedup_vs_reference_eager_gpu"] = round(layer["reference_eager_gpu"]["ms_fwd_bwd"] /
+                                                                layer["b200_fused_model"]["ms_fwd_bwd"], 2)
+            if dist is not None:
+                dist.barrier()
+
+            def qat_arm(quant, fm, steps_):
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+                r = QB.time_qat_step(quant, cfg7, seq=2048, bsz=1, warmup=3, steps=steps_, device=device, rank=rank,
+                                     world=world, autocast=True,   # the recipe: HF's Trainer runs the step in autocast(bf16)
+                                     fused=fm, bucket_cap_mb=args.bucket_cap_mb)
+                ms = reduce_max(r["ms_per_step"])
+                return dict(r, ms_per_step=round(ms, 2), tokens_per_s=round(world * 2048 / ms * 1e3), n_gpus=world)
+
+            qat = qat_arm(llm_qat_b200.utils_quant, True, nst)
+            qat["model"] = (("LLaMA-13B dims, random init, student W4A8KV8" if args.qat_model == "13b" else
+                             "LLaMA-7B dims, random init, student W4A8KV4") + " + frozen FP teacher, KD (KL batchmean), "
+                            "grad checkpointing, AdamW, bf16 inside torch.autocast(bf16) as kd_trainer.py:106 does; "
+                            "llm_qat_b200.fuse_model + fused KD loss" + (", DDP/NCCL all-reduce" if world > 1 else ""))
+            if not args.no_comparators:
+                qat["quant_path_only"] = qat_arm(llm_qat_b200.utils_quant, False, max(3, nst // 2))
+                qat["reference_eager_gpu"] = qat_arm(RM, False, max(3, nst // 2))
+                qat["reference_eager_gpu"]["what"] = ("same harness, same N, the reference's eager op chain "
+                                                      "(oracle/ref_module.py) on the GPU")
+                qat["speedup_vs_reference_eager_gpu"] = round(qat["reference_eager_gpu"]["ms_per_step"] / qat["ms_per_step"], 2)
         except Exception as e:  # keep the headline line even if the big model cannot run
             qat = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.synchronize()
@@ -599,15 +760,13 @@ def run_b200(args):
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": STEP_BYTES, "l2": "inputs larger than L2 "
-                   "(x+W = 157 MB per step, 786 MB touched between re-reads)",
-                   "parallelism": f"dp{world}: every rank fake-quantizes its own 8192-token batch and weight "
-                                  "replica; rows are independent, no data-path collective",
-                   "launch": "CUDA graph of one step, replayed K times" if used_graph else "direct launches"},
+        "config": bench_config(world),
+        "launch": "CUDA graph of one step, replayed K times" if used_graph else "direct launches",
         "gpu_launches": launches,
         "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     line.update(extras)
+    line["config3_layer"] = layer
     line["qat_step"] = qat
     print(json.dumps(line), flush=True)
 
@@ -652,18 +811,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     hx, hw, hgx, hgw = make_inputs(1234)
-    K, W = args.steps, max(args.warmup, 1)
-    K = min(K, 20)  # bounded: ~0.5 s per step on 8 cores
-    cb = run_cpu_port(hx, hw, hgx, hgw, budget_s=0.0, steps=K, warmup=min(W, 3))
+    K, W = args.steps, max(args.warmup, 3)      # the same K / W the b200 arm reports (~0.1-0.3 s per step)
+    cb = run_cpu_port(hx, hw, hgx, hgw, budget_s=0.0, steps=K, warmup=W)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))), "steps": K, "warmup": min(W, 3),
+        "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": STEP_BYTES,
-                   "note": "reference's torch CPU path (oracle/torch_chain.py port; /root/reference cannot "
-                           "travel to the GPU box), all host threads, rank 0 only"},
+        "config": bench_config(world),
+        "arm_note": "reference's torch CPU path (oracle/torch_chain.py port; /root/reference cannot travel to the "
+                    "GPU box), all host threads, rank 0 only",
         "gpu_launches": 0,
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -680,6 +839,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qat-step", action="store_true", help="skip the LLaMA-7B QAT-step extra (config 4)")
     ap.add_argument("--qat-layers", type=int, default=32)
+    ap.add_argument("--no-comparators", action="store_true",
+                    help="skip the reference-eager-GPU and quant-path-only arms of the QAT step")
+    ap.add_argument("--bucket-cap-mb", type=int, default=None, help="DDP gradient bucket size of the QAT step")
     ap.add_argument("--shape-sweep", action="store_true",
                     help="add per-shape / per-dtype / per-quantizer kernel timings (SURVEY.md 8d config 1)")
     ap.add_argument("--qat-model", default="7b", choices=["7b", "13b"],
