@@ -175,6 +175,16 @@ int qat_qlinear_fused_fwd(const void* x, const void* w, void* out, int8_t* qx, f
                           void* stream);
 
 /*
+ * The GEMM feed of a [rows, cols] tensor alone — what qat_qlinear_fused_fwd runs on each operand:
+ * SymQuantizer's codes (int8), dequant divisors e = fl(s + 1e-6) (NaN for a row whose abs-max is inf, so
+ * that the contraction returns NaN like the reference) and the packed STE mask (may be NULL).  Used to
+ * quantize a weight by output-channel shard: rows are independent, so a row range of W gives the same
+ * bits as the same rows of the full call (BASELINE configs[4]).
+ */
+int qat_sym_feed(const void* x, int8_t* codes, float* row_e, uint8_t* mask, float clip_lo, float clip_hi,
+                 int64_t rows, int64_t cols, int dtype, int bits, void* stream);
+
+/*
  * Rebuild the fake-quantized tensor from K1's int8 codes and row divisors:
  * out[r,c] = fl(codes[r,c] / row_e[r]) — bit-identical to qat_sym_fwd's y
  * (utils_quant.py:72) wherever the int8 feed did not saturate.  cols % 16 == 0.

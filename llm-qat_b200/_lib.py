@@ -45,6 +45,8 @@ def _declare(lib):
         "qat_set_gemm_cta_group": (I, [I]),
         "qat_set_pdl": (I, [I]),
         "qat_set_asym_div": (I, [I]),
+        # x, codes, row_e, mask, lo, hi, rows, cols, dtype, bits, stream
+        "qat_sym_feed": (I, [P, P, P, P, F, F, L, L, I, I, P]),
         # seed, rows, per_row, bf16_operands, dev_counters, stream
         "qat_selftest_fastdiv": (I, [c_uint64, L, I, I, P, P]),
         # x, w, out, qx, ex, mx, qw, ew, mw, T, N, K, dtype, a_bits, w_bits, lo, hi, reuse_x, reuse_w, stream

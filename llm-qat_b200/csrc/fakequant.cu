@@ -980,6 +980,13 @@ int qat_asym_fwd(const void* x, void* y, void* codes, int codes_kind, float* row
                                cols, dtype, bits, workspace, workspace_bytes, stream);
 }
 
+int qat_sym_feed(const void* x, int8_t* codes, float* row_e, uint8_t* mask, float clip_lo, float clip_hi,
+                 int64_t rows, int64_t cols, int dtype, int bits, void* stream) {
+  QAT_CHECK_ARG(codes != nullptr && row_e != nullptr, "codes / row_e must be provided");
+  QAT_CHECK_ARG(bits >= 2 && bits <= 8, "int8 codes need 2 <= bits <= 8 (got %d)", bits);
+  return qat::sym_fwd_feed(x, codes, row_e, mask, clip_lo, clip_hi, rows, cols, dtype, bits, stream);
+}
+
 int qat_set_asym_div(int mode) {
   QAT_CHECK_ARG(mode == QAT_ASYM_DIV_TRUE || mode == QAT_ASYM_DIV_RECIP, "mode must be QAT_ASYM_DIV_TRUE or QAT_ASYM_DIV_RECIP");
   qat::g_asym_div = mode;

@@ -50,6 +50,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import sharding as _sharding
 from ._lib import CODES_I8, CODES_I16, CODES_NONE, QAT_BF16, QAT_BF16_AMP, QAT_F32, check
 
 __all__ = ["SymQuantizer", "AsymQuantizer", "QuantizeLinear"]
@@ -410,6 +411,19 @@ class _QuantLinearFn(torch.autograd.Function):
         xe, xm, _ = _feed_layout(T, K)
         we, wm, _ = _feed_layout(N, K)
         xb, wb = xblob.data_ptr(), wblob.data_ptr()
+        if not reuse_w:
+            sh = _sharding.weight_sharding()
+            if sh is not None and _sharding.shardable(N, K, sh[1]):
+                # BASELINE configs[4]: this rank quantizes its out/world output channels, then the codes,
+                # divisors and masks (1.125 B/elem) are all-gathered over NVLink
+                group, world, rank = sh
+                n = N // world
+                with _on(dev):
+                    check(_lib.lib().qat_sym_feed(w.data_ptr() + rank * n * K * w.element_size(),
+                                                  wb + rank * n * K, wb + we + rank * n * 4, wb + wm + rank * n * K // 8,
+                                                  -2.0, 2.0, n, K, dt, int(w_bits), stream), "qat_sym_feed")
+                _sharding.all_gather_feed(wblob, N, K, group, world, rank)
+                reuse_w = 1
         with _on(dev):
             rc = _lib.lib().qat_qlinear_fused_fwd(
                 x2.data_ptr(), w.data_ptr(), out.data_ptr(), xb, xb + xe, xb + xm, wb, wb + we, wb + wm,

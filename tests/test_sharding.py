@@ -78,3 +78,56 @@ def test_two_rank_gloo_shards_reassemble(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert bool(np.load(tmp_path / f"ok{r}.npy")[0])
+
+
+# ---- BASELINE configs[4]: weights quantized by output-channel shard, codes / divisors / masks all-gathered
+def _feed_worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from llm_qat_b200 import sharding as S
+    from llm_qat_b200.utils_quant import _feed_layout, _feed_views
+    from oracle import quant_oracle as qo
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S.enable_weight_sharding()
+    assert S.weight_sharding()[1:] == (world, rank)
+    N, K = 64, 128
+    g = torch.Generator().manual_seed(77)
+    w = (torch.randn(N, K, generator=g) * 0.7).bfloat16().float()      # identical on every rank
+    assert S.shardable(N, K, world) and not S.shardable(N + 1, K, world)
+
+    def feed_of(rows_tensor):     # what qat_sym_feed writes for these rows (oracle stands in for the kernel)
+        o = qo.sym_forward(rows_tensor.numpy(), 4, False, "bf16")
+        m = qo.ste_backward(np.ones_like(rows_tensor.numpy()), rows_tensor.numpy(), -2.0, 2.0, "bf16")["mask"]
+        return (torch.from_numpy(np.clip(o["codes"], -128, 127).astype(np.int8)), torch.from_numpy(o["e"].astype(np.float32)),
+                torch.from_numpy(qo.pack_mask(m)))
+
+    blob = torch.zeros(_feed_layout(N, K)[2], dtype=torch.uint8)
+    n = N // world
+    codes, e, mask = feed_of(w[rank * n:(rank + 1) * n])
+    for (whole, mine), src in zip(S.feed_slices(blob, N, K, world, rank), (codes, e, mask)):
+        mine.copy_(src.contiguous().view(-1).view(torch.uint8))
+    S.all_gather_feed(blob, N, K, *S.weight_sharding())
+    full = torch.zeros_like(blob)
+    c, e2, m2 = _feed_views(full, N, K)
+    fc, fe, fm = feed_of(w)
+    c.copy_(fc)
+    e2.copy_(fe)
+    m2.copy_(fm)
+    ok = torch.equal(blob, full)
+    S.disable_weight_sharding()
+    ok = ok and S.weight_sharding() is None
+    np.save(os.path.join(out_dir, f"feed_ok{rank}.npy"), np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_weight_feed_shards_all_gather_to_the_unsharded_blob(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_feed_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert bool(np.load(tmp_path / f"feed_ok{r}.npy")[0])
