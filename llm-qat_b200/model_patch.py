@@ -73,6 +73,20 @@ def _rope_tables(self, seq_len: int, device):
     return tabs
 
 
+def _module_clip(self):
+    """(lo, hi) of act_clip_val_k, read once per tensor version: a clip tensor that lives on the GPU (a model
+    built under `with torch.device("cuda")`) would otherwise cost a device-to-host sync in every forward."""
+    t = getattr(self, "act_clip_val_k", None)
+    if t is None:
+        return (-2.0, 2.0)
+    key = (id(t), t._version)
+    cached = self.__dict__.get("_qat_clip")
+    if cached is None or cached[0] != key:
+        cached = (key, _clip_bounds(t))
+        self.__dict__["_qat_clip"] = cached
+    return cached[1]
+
+
 def _attention_forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                        output_attentions=False, use_cache=False):
     orig = self._qat_orig_forward
@@ -91,7 +105,7 @@ def _attention_forward(self, hidden_states, attention_mask=None, position_ids=No
         return orig(hidden_states, attention_mask, position_ids, past_key_value, output_attentions, use_cache)
     pos = position_ids.expand(bsz, q_len) if position_ids.shape[0] != bsz else position_ids
     kv_bits = int(getattr(self, "kv_bits", 32))     # a stock (teacher) LlamaAttention has no K/V fake-quant
-    clip = _clip_bounds(self.act_clip_val_k) if hasattr(self, "act_clip_val_k") else (-2.0, 2.0)
+    clip = _module_clip(self)
     qr, kr, vq = F.qkv_prep(q, k, v, cos, sin, pos, self.num_heads, kv_bits, clip)
     shape = (bsz, q_len, self.num_heads, self.head_dim)
     o = F.causal_attention(qr.view(shape), kr.view(shape), vq.view(shape), causal=True)
