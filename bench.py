@@ -846,7 +846,13 @@ def main():
                     help="add per-shape / per-dtype / per-quantizer kernel timings (SURVEY.md 8d config 1)")
     ap.add_argument("--qat-model", default="7b", choices=["7b", "13b"],
                     help="model of the QAT-step extra: 7b = BASELINE configs[3], 13b = configs[4] (W4A8KV8)")
+    ap.add_argument("--hang-dump-s", type=int, default=int(os.environ.get("BENCH_HANG_DUMP_S", "600")),
+                    help="dump every thread's stack and exit if the run is still going after this many seconds")
     args = ap.parse_args()
+    import faulthandler
+
+    # a stuck collective must not sit there until the driver's limit: report where each rank is and exit
+    faulthandler.dump_traceback_later(args.hang_dump_s, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
