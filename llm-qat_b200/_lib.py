@@ -89,9 +89,42 @@ def _declare(lib):
     return sig
 
 
+# Programmatic dependent launch x CUPTI.  With a CUPTI activity trace attached (torch.profiler / kineto),
+# a stream of PDL launches of this library's persistent one-CTA-per-SM kernels can stop making progress:
+# tests/gpu_pdl_profiler_soak.py reproduces it on B200 / driver 580 (1 of 20 traces of a decoder layer's
+# fwd+bwd never returned from cudaDeviceSynchronize with PDL forced on; 0 of 20 with plain stream order;
+# never without a tracer).  PDL buys ~1.5 us per launch and nothing else, so it is switched off for as long
+# as a torch profiler is active (checked on every entry to lib(): one C++ bool read) and when the process
+# was started under an injected profiler (Nsight Systems / Compute set CUDA_INJECTION64_PATH).
+# QAT_B200_PDL=0 always off, =force never auto-disabled (what the soak tool uses to reproduce the hang).
+_pdl_mode = os.environ.get("QAT_B200_PDL", "1").strip().lower()
+_pdl_user_on = _pdl_mode != "0"
+_pdl_auto = _pdl_user_on and _pdl_mode != "force"
+_pdl_suppressed = False
+_INJECTED = any(os.environ.get(k) for k in ("CUDA_INJECTION64_PATH", "NSYS_PROFILING_SESSION_ID",
+                                             "NV_COMPUTE_PROFILER_PERFWORKS_DIR"))
+try:
+    from torch.autograd import _profiler_enabled as _torch_profiler_enabled
+except Exception:  # pragma: no cover - torch without the symbol
+    def _torch_profiler_enabled():
+        return False
+
+
+def _sync_pdl_with_profiler(handle) -> None:
+    global _pdl_suppressed
+    want_off = _INJECTED or _torch_profiler_enabled()
+    if want_off != _pdl_suppressed:
+        handle.qat_set_pdl(0 if want_off else 1)
+        _pdl_suppressed = want_off
+
+
 def lib():
     """The loaded library; raises ImportError with build instructions if absent."""
     global _lib
+    if _lib is not None:
+        if _pdl_auto:
+            _sync_pdl_with_profiler(_lib)
+        return _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError(
@@ -100,7 +133,11 @@ def lib():
                 "llm-qat_b200 has no CPU or PyTorch fallback.")
         handle = ctypes.CDLL(LIB_PATH)
         _declare(handle)
+        if _pdl_mode == "force":
+            handle.qat_set_pdl(1)
         _lib = handle
+        if _pdl_auto:
+            _sync_pdl_with_profiler(_lib)
     return _lib
 
 

@@ -33,6 +33,10 @@ bool pdl_enabled() {
   if (v < 0) {
     const char* e = getenv("QAT_B200_PDL");
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    // started under an injected CUPTI client (Nsight Systems / Compute): plain stream order, see _lib.py
+    if (v == 1 && !(e != nullptr && e[0] == 'f') &&
+        (getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NSYS_PROFILING_SESSION_ID") != nullptr))
+      v = 0;
     g_pdl.store(v, std::memory_order_relaxed);
   }
   return v != 0;

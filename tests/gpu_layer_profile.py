@@ -6,7 +6,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import faulthandler
 # one run of this tool under torch.profiler (CUPTI tracing) with programmatic dependent launch on did not
 # return (not reproduced in five later runs, tests/gpu_profiler_check.py passes): trace with plain stream order
-os.environ.setdefault("QAT_B200_PDL", "0")
 faulthandler.dump_traceback_later(int(os.environ.get('PROFILE_TOOL_TIMEOUT', '240')), exit=True)   # a stuck run reports where
 import torch
 from torch.profiler import profile, ProfilerActivity
