@@ -226,6 +226,8 @@ int qat_gemm_bf16_debug_strides(uint32_t lbo_bytes, uint32_t sbo_bytes);
  */
 int qat_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
                  int head_dim, float softmax_scale, int causal, void* stream);
+/* Test hook: clock64() trace of one CTA of the forward kernel (3 roles x 16 tiles x 8 events, int64). */
+int qat_attn_debug_trace(long long* dev_buffer);
 int qat_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                  float* delta, void* dq, void* dk, void* dv, int B, int S, int H, int head_dim,
                  float softmax_scale, int causal, void* stream);

@@ -77,6 +77,7 @@ def _declare(lib):
         "qat_qkv_prep_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, F, F, I, P]),
         # dq_rot, dk_rot, dv_q, kmask, vmask, cos, sin, pos, dq, dk, dv, tokens, heads, head_dim, stream
         "qat_qkv_prep_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, I, P]),
+        "qat_attn_debug_trace": (I, [P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream
         "qat_sym_fwd_bwd_host": (I, [P, P, P, P, F, F, L, L, I, I, P, Z, P]),

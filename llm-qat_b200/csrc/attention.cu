@@ -11,15 +11,15 @@
 // Layout: Q, K, V, O, dO, dQ, dK, dV are bf16 [B, S, H, D] (the projections' own layout:
 // [b, s, hidden] viewed as heads — no transposes), D == 128.  LSE and delta are fp32 [B, H, S].
 //
-// Forward, one CTA per (128-query tile, head, batch), 192 threads:
+// Forward, one CTA per (128-query tile, head, batch), 320 threads:
 //   warp 0   TMA producer: Q once, K/V tiles of 128 keys through a 2-stage ring
-//   warp 1   MMA issuer:   S[buf] = Q K_j^T  (M128 N128 K128, both K-major) issued one tile ahead
-//                          O     += P_j V_j  (A = P from shared memory, B = V MN-major)
-//   warps 2-5 softmax:     one thread per query row (a TMEM lane): tcgen05.ld S, running max / sum in
-//                          registers (no shuffles), P -> bf16 -> 128B-swizzled shared memory,
-//                          lazy rescale of O in TMEM (only when the row max grew by > 2^8),
-//                          epilogue O / l -> bf16, LSE.
-//   TMEM: S0 | S1 | O = 384 columns.
+//   warp 1   MMA issuer:   S[b] = Q K_j^T  (M128 N128 K128, both K-major) issued two tiles ahead
+//                          O[b] += P_j V_j (A = P from shared memory, B = V MN-major),  b = j % 2
+//   warps 2-5, 6-9         two softmax warpgroups, tile parity b each: one thread per query row (a TMEM
+//                          lane): tcgen05.ld S, running max / sum in registers (no shuffles), P -> bf16 ->
+//                          128B-swizzled shared memory, lazy rescale of O[b] in TMEM (only when the row max
+//                          grew by > 2^8); the two partial soft-maxes are merged in the epilogue.
+//   TMEM: S0 | S1 | O0 | O1 = 512 columns.
 // Backward: attn_delta (rowsum(dO * O)), then two kernels without atomics —
 //   attn_bwd_dq   (query-stationary, 64-key steps):  S, dP -> dS -> dQ += dS K
 //   attn_bwd_dkv  (key-stationary, 64-query steps):  S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
@@ -63,7 +63,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+// Debug hook (tests/gpu_attn_trace.py): when set, CTA (0,0,0) of attn_fwd_kernel records clock64() at its
+// phase boundaries — slots [role][tile][event] of a device buffer — so the per-tile critical path can be
+// read off instead of guessed.  NULL in normal operation (one predictable branch per event).
+long long* g_attn_trace = nullptr;
+constexpr int kTraceTiles = 16, kTraceEvents = 8;
+
 struct AttnParams {
+  long long* trace;
   void* o;             // fwd: O [B,S,H,D] bf16
   float* lse;          // [B,H,S] natural-log LSE of the scaled scores
   const float* delta;  // bwd: rowsum(dO * O) [B,H,S]
@@ -78,16 +85,22 @@ struct AttnParams {
 // =============================================================================================
 // forward
 // =============================================================================================
+// Two softmax warpgroups per CTA, each with its OWN running (max, sum), S buffer, P buffer and O
+// accumulator: warpgroup b takes the key tiles j with j % 2 == b, so its soft-max of tile j runs
+// while the tensor core does Q K_{j+1}^T and P_{j-1} V_{j-1} of the other warpgroup, and the two
+// partial results are merged once at the end (split-KV inside the CTA).  One thread per query
+// row: row max / sum never leave registers.
 namespace fwd {
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-5 WG0, warps 6-9 WG1
 constexpr uint32_t kTile = BM * D * 2;              // 32 KB: [128][128] bf16 as 2 chunks of 16 KB
 constexpr uint32_t kChunk = BM * 128;               // 16 KB
-constexpr uint32_t oQ = 0, oK = kTile, oV = 3 * kTile, oP = 5 * kTile, oBar = 6 * kTile;
-enum { bQ = 0, bKfull = 1, bKempty = 3, bVfull = 5, bVempty = 7, bSfull = 9, bSfree = 11, bPfull = 13, bPVdone = 14,
-       nBars = 15 };
+constexpr uint32_t oQ = 0, oK = kTile, oV = 3 * kTile, oP = 5 * kTile, oBar = 7 * kTile;
+enum { bQ = 0, bKfull = 1, bKempty = 3, bVfull = 5, bVempty = 7, bSfull = 9, bSfree = 11, bPfull = 13, bPVdone = 15,
+       nBars = 17 };
 constexpr uint32_t oTmem = oBar + 8 * nBars;
 constexpr uint32_t kSmem = oTmem + 16 + 1024;
 static_assert(kSmem <= 232448, "smem");
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512)
 }  // namespace fwd
 
 __global__ void __launch_bounds__(fwd::kThreads, 1)
@@ -103,6 +116,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int q0 = q_tile * BM;
   const int n_kv = p.causal ? min((q0 + BM + BM - 1) / BM, (p.S + BM - 1) / BM) : (p.S + BM - 1) / BM;
   auto bar = [&](int i) { return base + oBar + 8u * (uint32_t)i; };
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  // role 0 = MMA thread, 1 = warpgroup 0 (thread 64), 2 = warpgroup 1 (thread 192)
+  auto trace = [&](int role, int tile, int ev) {
+    if (tracing && tile < kTraceTiles) p.trace[(role * kTraceTiles + tile) * kTraceEvents + ev] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_q);
@@ -116,9 +134,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(bar(bVempty + s), 1);
       mbar_init(bar(bSfull + s), 1);
       mbar_init(bar(bSfree + s), 128);
+      mbar_init(bar(bPfull + s), 128);
+      mbar_init(bar(bPVdone + s), 1);
     }
-    mbar_init(bar(bPfull), 128);
-    mbar_init(bar(bPVdone), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc_cg1<512>(base + oTmem);
@@ -135,29 +153,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_expect_tx(bar(bQ), kTile);
       tma_load_3d(base + oQ, &map_q, bar(bQ), col, q0, b);
       tma_load_3d(base + oQ + kChunk, &map_q, bar(bQ), col + 64, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
+      // K_j is wanted two tiles ahead of V_j (Q K^T is issued two tiles early, P V only after the soft-max),
+      // and its stage frees as soon as Q K_{j-2}^T retires — so K loads run one tile ahead of the V loads
+      // instead of queueing behind a V stage that is still in use (measured: 1300 cycles of exposed TMA
+      // latency per tile with the K_j, V_j, K_{j+1}, V_{j+1} order; tests/gpu_attn_trace.py)
+      auto load_k = [&](int j) {
         const int s = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        mbar_wait(bar(bKempty + s), ph ^ 1u);
+        mbar_wait(bar(bKempty + s), (uint32_t)((j >> 1) & 1) ^ 1u);
         mbar_expect_tx(bar(bKfull + s), kTile);
         tma_load_3d(base + oK + s * kTile, &map_k, bar(bKfull + s), col, j * BM, b);
         tma_load_3d(base + oK + s * kTile + kChunk, &map_k, bar(bKfull + s), col + 64, j * BM, b);
-        mbar_wait(bar(bVempty + s), ph ^ 1u);
+      };
+      auto load_v = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(bar(bVempty + s), (uint32_t)((j >> 1) & 1) ^ 1u);
         mbar_expect_tx(bar(bVfull + s), kTile);
         tma_load_3d(base + oV + s * kTile, &map_v, bar(bVfull + s), col, j * BM, b);
         tma_load_3d(base + oV + s * kTile + kChunk, &map_v, bar(bVfull + s), col + 64, j * BM, b);
+      };
+      load_k(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) load_k(j + 1);
+        load_v(j);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BM, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, 0, 1);
+      // tile j uses K/V stage, S buffer, P buffer and O accumulator (j & 1); its use count is j >> 1
       auto issue_qk = [&](int j) {
         const int s = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        trace(0, j, 0);
         mbar_wait(bar(bKfull + s), ph);
-        mbar_wait(bar(bSfree + s), ph ^ 1u);     // softmax drained this S buffer's previous use
+        trace(0, j, 1);
+        mbar_wait(bar(bSfree + s), ph ^ 1u);     // the warpgroup drained this S buffer's previous use
         tcgen05_fence_after();
+        trace(0, j, 2);
         const uint32_t d_s = tmem + (uint32_t)(s * BM);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
@@ -165,46 +198,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                       idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(bar(bKempty + s));
         umma_commit(bar(bSfull + s));
+        trace(0, j, 3);
       };
       mbar_wait(bar(bQ), 0);
       issue_qk(0);
+      if (n_kv > 1) issue_qk(1);
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_qk(j + 1);
         const int s = j & 1;
-        mbar_wait(bar(bVfull + s), (uint32_t)((j >> 1) & 1));
-        mbar_wait(bar(bPfull), (uint32_t)(j & 1));
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        // S[s] is free as soon as its warpgroup has pulled tile j into registers: queue Q K_{j+2}^T now,
+        // so that it runs under that warpgroup's soft-max of tile j
+        if (j + 2 < n_kv) issue_qk(j + 2);
+        trace(0, j, 4);
+        mbar_wait(bar(bVfull + s), ph);
+        trace(0, j, 5);
+        mbar_wait(bar(bPfull + s), ph);
         tcgen05_fence_after();
-        const uint32_t d_o = tmem + 2u * BM;
+        trace(0, j, 6);
+        const uint32_t d_o = tmem + 2u * BM + (uint32_t)(s * D);
 #pragma unroll
         for (int k = 0; k < BM / 16; ++k)
-          umma_f16<1>(d_o, desc_k_step(base + oP, kChunk, k), desc_mn_step(base + oV + s * kTile, kChunk, k),
-                      idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_f16<1>(d_o, desc_k_step(base + oP + s * kTile, kChunk, k), desc_mn_step(base + oV + s * kTile, kChunk, k),
+                      idesc_pv, (j > 1 || k > 0) ? 1u : 0u);
         umma_commit(bar(bVempty + s));
-        umma_commit(bar(bPVdone));
+        umma_commit(bar(bPVdone + s));
+        trace(0, j, 7);
       }
     }
   } else {
-    // ===================== softmax: one thread per query row =====================
-    const int quad = warp & 3;
+    // ===================== two softmax warpgroups: one thread per query row =====================
+    const int wg = (warp - 2) >> 2;                 // 0 | 1: takes the key tiles j with (j & 1) == wg
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
     const int q_idx = q0 + r;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_s = t_lane + (uint32_t)(wg * BM), t_o = t_lane + 2u * BM + (uint32_t)(wg * D);
+    const uint32_t p_buf = base + oP + (uint32_t)wg * kTile;
     const float c = p.scale * kLog2e;
     float m_run = -INFINITY;   // running max of the raw scores (the one the exponent is taken against)
     float l_run = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int s = j & 1;
-      mbar_wait(bar(bSfull + s), (uint32_t)((j >> 1) & 1));
+    int uses = 0;
+    const bool tr = (threadIdx.x == 64 || threadIdx.x == 192);
+    for (int j = wg; j < n_kv; j += 2, ++uses) {
+      const uint32_t ph = (uint32_t)(uses & 1);
+      if (tr) trace(1 + wg, j, 0);
+      mbar_wait(bar(bSfull + wg), ph);
       tcgen05_fence_after();
+      if (tr) trace(1 + wg, j, 1);
       uint32_t sv[128];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]);
-        tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * BM + ch * 32), dst);
+        tmem_ld_32x32b_x32(t_s + (uint32_t)(ch * 32), dst);
       }
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(bar(bSfree + s));
+      mbar_arrive(bar(bSfree + wg));
+      if (tr) trace(1 + wg, j, 2);
       const int k0 = j * BM;
       const bool edge = (p.causal && k0 + BM - 1 > q0) || (k0 + BM > p.S);
       float mx = -INFINITY;
@@ -222,8 +272,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^8 in the
       // exponent (p <= 256 stays exact enough in bf16 and far from fp32 overflow)
+      if (tr) trace(1 + wg, j, 3);
       const float m_new = fmaxf(m_run, mx);
-      const bool grow = (m_new - m_run) * c > 8.0f;     // false for NaN; true on the first tile (m_run = -inf)
+      const bool grow = (m_new - m_run) * c > 8.0f;     // true on this warpgroup's first tile (m_run = -inf)
       const float m_use = grow ? m_new : m_run;
       const float alpha = grow ? ex2f((m_run - m_use) * c) : 1.0f;   // first tile: ex2(-inf) = 0
       const float mc = m_use * c;
@@ -238,55 +289,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       l_run = l_run * alpha + sum;
       m_run = m_use;
-      if (j > 0) {
-        mbar_wait(bar(bPVdone), (uint32_t)((j - 1) & 1));   // O is quiescent, P buffer free
+      if (tr) trace(1 + wg, j, 4);
+      if (uses > 0) {
+        mbar_wait(bar(bPVdone + wg), ph ^ 1u);      // this warpgroup's O is quiescent, its P buffer free
         tcgen05_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
           for (int ch = 0; ch < 4; ++ch) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(t_lane + (uint32_t)(2 * BM + ch * 32), o);
+            tmem_ld_32x32b_x32(t_o + (uint32_t)(ch * 32), o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(t_lane + (uint32_t)(2 * BM + ch * 32), o);
+            tmem_st_32x32b_x32(t_o + (uint32_t)(ch * 32), o);
           }
           tmem_st_wait();
         }
       }
+      if (tr) trace(1 + wg, j, 5);
 #pragma unroll
       for (int u = 0; u < 16; ++u)
-        sts128(base + oP + (uint32_t)(u >> 3) * kChunk + swz((uint32_t)r, (uint32_t)(u & 7)), pk[4 * u], pk[4 * u + 1],
+        sts128(p_buf + (uint32_t)(u >> 3) * kChunk + swz((uint32_t)r, (uint32_t)(u & 7)), pk[4 * u], pk[4 * u + 1],
                pk[4 * u + 2], pk[4 * u + 3]);
+      if (tr) trace(1 + wg, j, 6);
       fence_proxy_async_smem();
       tcgen05_fence_before();
-      mbar_arrive(bar(bPfull));
+      mbar_arrive(bar(bPfull + wg));
+      if (tr) trace(1 + wg, j, 7);
     }
-    // epilogue: O / l -> bf16 [B,S,H,D]; LSE
-    mbar_wait(bar(bPVdone), (uint32_t)((n_kv - 1) & 1));
-    tcgen05_fence_after();
-    const float inv_l = 1.0f / l_run;
+    // ---- merge the two warpgroups' partial soft-maxes: stats through shared memory (their own, now idle,
+    //      P buffers), then warpgroup b writes output columns [64 b, 64 b + 64)
+    if (uses > 0) {
+      mbar_wait(bar(bPVdone + wg), (uint32_t)((uses - 1) & 1));
+      tcgen05_fence_after();
+    }
+    float2* stats = reinterpret_cast<float2*>(base_ptr + oP + (uint32_t)wg * kTile);
+    stats[r] = make_float2(m_run, l_run);
+    named_bar_sync(1, 256);
+    const float2 other = reinterpret_cast<const float2*>(base_ptr + oP + (uint32_t)(wg ^ 1) * kTile)[r];
+    const float m0 = wg == 0 ? m_run : other.x, l0 = wg == 0 ? l_run : other.y;
+    const float m1 = wg == 0 ? other.x : m_run, l1 = wg == 0 ? other.y : l_run;
+    const bool has1 = n_kv > 1;                      // warpgroup 1 saw at least one tile (its O1 is defined)
+    const float m = has1 ? fmaxf(m0, m1) : m0;
+    const float w0 = ex2f((m0 - m) * c), w1 = has1 ? ex2f((m1 - m) * c) : 0.f;
+    const float l = l0 * w0 + l1 * w1;
+    const float f0 = w0 / l, f1 = w1 / l;
     const bool live = q_idx < p.S;
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.o) + (((int64_t)b * p.S + q_idx) * p.H + h) * D;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.o) + (((int64_t)b * p.S + q_idx) * p.H + h) * D + wg * 64;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(t_lane + (uint32_t)(2 * BM + ch * 32), o);
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(2 * BM + wg * 64 + ch * 32), o0);
+      if (has1) tmem_ld_32x32b_x32(t_lane + (uint32_t)(2 * BM + D + wg * 64 + ch * 32), o1);
       tmem_ld_wait();
       if (live) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = __uint_as_float(o0[i]) * f0;
+          if (has1) v[i] = fmaf(__uint_as_float(o1[i]), f1, v[i]);
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + ch * 32 + i) = v;
+          uint4 q4;
+          q4.x = pack_bf16x2(v[i], v[i + 1]);
+          q4.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          q4.z = pack_bf16x2(v[i + 4], v[i + 5]);
+          q4.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(orow + ch * 32 + i) = q4;
         }
       }
     }
-    if (live && p.lse != nullptr)
-      p.lse[((int64_t)b * p.H + h) * p.S + q_idx] = m_run * p.scale + logf(l_run);
+    if (wg == 0 && live && p.lse != nullptr)
+      p.lse[((int64_t)b * p.H + h) * p.S + q_idx] = m * p.scale + logf(l);
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -326,19 +401,23 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // backward: dQ  (query-stationary; 64-key steps)
 // =============================================================================================
 namespace bq {
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                        // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9: two warpgroups, each thread
+                                                     // owns one query row and HALF of the step's 64 key columns
 constexpr int BN = 64;                               // keys per step
 constexpr uint32_t kTileQ = BM * D * 2;              // 32 KB (2 chunks of 16 KB)
 constexpr uint32_t kChunkQ = BM * 128;               // 16 KB
 constexpr uint32_t kTileK = BN * D * 2;              // 16 KB (2 chunks of 8 KB)
 constexpr uint32_t kChunkK = BN * 128;               // 8 KB
 constexpr uint32_t kTileS = BM * BN * 2;             // 16 KB: dS [128][64] bf16, one chunk
-constexpr uint32_t oQ = 0, oDO = kTileQ, oK = 2 * kTileQ, oV = oK + 2 * kTileK, oDS = oV + 2 * kTileK,
+constexpr int KS = 4;                                // K / V ring depth: K_j is held until dQ += dS_j K_j retires,
+                                                     // i.e. through the whole soft-max of step j
+constexpr uint32_t oQ = 0, oDO = kTileQ, oK = 2 * kTileQ, oV = oK + KS * kTileK, oDS = oV + KS * kTileK,
                    oBar = oDS + 2 * kTileS;
-enum { bQ = 0, bKfull = 1, bKempty = 3, bVfull = 5, bVempty = 7, bSPfull = 9, bSPfree = 11, bDSfull = 13,
-       bDSfree = 15, bDone = 17, nBars = 18 };
+enum { bQ = 0, bKfull = 1, bKempty = bKfull + KS, bVfull = bKempty + KS, bVempty = bVfull + KS, bSPfull = bVempty + KS,
+       bSPfree = bSPfull + 2, bDSfull = bSPfree + 2, bDSfree = bDSfull + 2, bDone = bDSfree + 2, nBars = bDone + 1 };
 constexpr uint32_t oTmem = oBar + 8 * nBars;
 constexpr uint32_t kSmem = oTmem + 16 + 1024;
+static_assert(kSmem <= 232448, "smem");
 // TMEM columns: S0 [0,64) dP0 [64,128) S1 [128,192) dP1 [192,256) dQ [256,384)
 }  // namespace bq
 
@@ -364,14 +443,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     prefetch_tensormap(&map_v);
     prefetch_tensormap(&map_do);
     mbar_init(bar(bQ), 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KS; ++s) {
       mbar_init(bar(bKfull + s), 1);
       mbar_init(bar(bKempty + s), 1);
       mbar_init(bar(bVfull + s), 1);
       mbar_init(bar(bVempty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar(bSPfull + s), 1);
-      mbar_init(bar(bSPfree + s), 128);
-      mbar_init(bar(bDSfull + s), 128);
+      mbar_init(bar(bSPfree + s), 256);
+      mbar_init(bar(bDSfull + s), 256);
       mbar_init(bar(bDSfree + s), 1);
     }
     mbar_init(bar(bDone), 1);
@@ -394,17 +475,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tma_load_3d(base + oDO, &map_do, bar(bQ), col, q0, b);
       tma_load_3d(base + oDO + kChunkQ, &map_do, bar(bQ), col + 64, q0, b);
       for (int j = 0; j < n_steps; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        // K[s] is read by S_j (K-major) and by dQ += dS_j K_j (MN-major): free after the latter
-        mbar_wait(bar(bKempty + s), ph ^ 1u);
-        mbar_expect_tx(bar(bKfull + s), kTileK);
-        tma_load_3d(base + oK + s * kTileK, &map_k, bar(bKfull + s), col, j * BN, b);
-        tma_load_3d(base + oK + s * kTileK + kChunkK, &map_k, bar(bKfull + s), col + 64, j * BN, b);
-        mbar_wait(bar(bVempty + s), ph ^ 1u);
-        mbar_expect_tx(bar(bVfull + s), kTileK);
-        tma_load_3d(base + oV + s * kTileK, &map_v, bar(bVfull + s), col, j * BN, b);
-        tma_load_3d(base + oV + s * kTileK + kChunkK, &map_v, bar(bVfull + s), col + 64, j * BN, b);
+        const int ks = j % KS;
+        const uint32_t ph = (uint32_t)((j / KS) & 1);
+        // K[ks] is read by S_j (K-major) and by dQ += dS_j K_j (MN-major): free after the latter
+        mbar_wait(bar(bKempty + ks), ph ^ 1u);
+        mbar_expect_tx(bar(bKfull + ks), kTileK);
+        tma_load_3d(base + oK + ks * kTileK, &map_k, bar(bKfull + ks), col, j * BN, b);
+        tma_load_3d(base + oK + ks * kTileK + kChunkK, &map_k, bar(bKfull + ks), col + 64, j * BN, b);
+        mbar_wait(bar(bVempty + ks), ph ^ 1u);
+        mbar_expect_tx(bar(bVfull + ks), kTileK);
+        tma_load_3d(base + oV + ks * kTileK, &map_v, bar(bVfull + ks), col, j * BN, b);
+        tma_load_3d(base + oV + ks * kTileK + kChunkK, &map_v, bar(bVfull + ks), col + 64, j * BN, b);
       }
     }
   } else if (warp == 1) {
@@ -412,42 +493,43 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);      // S / dP: M128 N64, K-major x K-major
       constexpr uint32_t idesc_dq = make_idesc_bf16(BM, D, 0, 1);      // dQ: M128 N128, B = K MN-major
       auto issue_sp = [&](int j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        mbar_wait(bar(bKfull + s), ph);
-        mbar_wait(bar(bVfull + s), ph);
+        const int s = j & 1, ks = j % KS;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1), kph = (uint32_t)((j / KS) & 1);
+        mbar_wait(bar(bKfull + ks), kph);
+        mbar_wait(bar(bVfull + ks), kph);
         mbar_wait(bar(bSPfree + s), ph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_s = tmem + (uint32_t)(s * 128), d_p = d_s + 64u;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_f16<1>(d_s, desc_k_step(base + oQ, kChunkQ, k), desc_k_step(base + oK + s * kTileK, kChunkK, k),
+          umma_f16<1>(d_s, desc_k_step(base + oQ, kChunkQ, k), desc_k_step(base + oK + ks * kTileK, kChunkK, k),
                       idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_f16<1>(d_p, desc_k_step(base + oDO, kChunkQ, k), desc_k_step(base + oV + s * kTileK, kChunkK, k),
+          umma_f16<1>(d_p, desc_k_step(base + oDO, kChunkQ, k), desc_k_step(base + oV + ks * kTileK, kChunkK, k),
                       idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar(bVempty + s));
+        umma_commit(bar(bVempty + ks));
         umma_commit(bar(bSPfull + s));
       };
       mbar_wait(bar(bQ), 0);
       issue_sp(0);
       for (int j = 0; j < n_steps; ++j) {
         if (j + 1 < n_steps) issue_sp(j + 1);
-        const int s = j & 1;
+        const int s = j & 1, ks = j % KS;
         mbar_wait(bar(bDSfull + s), (uint32_t)((j >> 1) & 1));
         tcgen05_fence_after();
         const uint32_t d_q = tmem + 256u;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)
           umma_f16<1>(d_q, make_smem_desc(base + oDS + s * kTileS + (uint32_t)k * 32u),
-                      desc_mn_step(base + oK + s * kTileK, kChunkK, k), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar(bKempty + s));
+                      desc_mn_step(base + oK + ks * kTileK, kChunkK, k), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar(bKempty + ks));
         umma_commit(bar(bDSfree + s));
       }
       umma_commit(bar(bDone));
     }
   } else {
+    const int wg = (warp - 2) >> 2;                 // which half of the step's key columns
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int q_idx = q0 + r;
@@ -457,49 +539,58 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int64_t stat = ((int64_t)b * p.H + h) * p.S + q_idx;
     const float lse_c = live ? p.lse[stat] * kLog2e : 0.f;
     const float dlt = live ? p.delta[stat] : 0.f;
+    const int c0 = wg * 32;
     for (int j = 0; j < n_steps; ++j) {
       const int s = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       mbar_wait(bar(bSPfull + s), ph);
       tcgen05_fence_after();
-      uint32_t sv[64], dp[64];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + ch * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
-        tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + 64 + ch * 32), *reinterpret_cast<uint32_t(*)[32]>(&dp[ch * 32]));
-      }
+      uint32_t sv[32], dp[32];
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + c0), sv);
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + 64 + c0), dp);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(bar(bSPfree + s));
-      const int k0 = j * BN;
-      uint32_t pk[32];
+      const int k0 = j * BN + c0;
+      const bool edge = (p.causal && j * BN + BN - 1 > q0) || (j * BN + BN > p.S) || (q0 + BM > p.S);
+      uint32_t pk[16];
+      if (edge) {
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        float ds[2];
+        for (int i = 0; i < 32; i += 2) {
+          float ds[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k_idx = k0 + i + e;
-          const bool dead = !live || k_idx >= p.S || (p.causal && k_idx > q_idx);
-          const float pr = ex2f(fmaf(__uint_as_float(sv[i + e]), c, -lse_c));
-          ds[e] = dead ? 0.f : pr * (__uint_as_float(dp[i + e]) - dlt) * p.scale;
+          for (int e = 0; e < 2; ++e) {
+            const int k_idx = k0 + i + e;
+            const bool dead = !live || k_idx >= p.S || (p.causal && k_idx > q_idx);
+            const float pr = ex2f(fmaf(__uint_as_float(sv[i + e]), c, -lse_c));
+            ds[e] = dead ? 0.f : pr * (__uint_as_float(dp[i + e]) - dlt) * p.scale;
+          }
+          pk[i >> 1] = pack_bf16x2(ds[0], ds[1]);
         }
-        pk[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2f(fmaf(__uint_as_float(sv[i]), c, -lse_c));
+          const float p1 = ex2f(fmaf(__uint_as_float(sv[i + 1]), c, -lse_c));
+          pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - dlt) * p.scale,
+                                   p1 * (__uint_as_float(dp[i + 1]) - dlt) * p.scale);
+        }
       }
       mbar_wait(bar(bDSfree + s), ph ^ 1u);        // the dQ MMA that read this dS buffer two steps ago is done
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        sts128(base + oDS + s * kTileS + swz((uint32_t)r, (uint32_t)u), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2],
-               pk[4 * u + 3]);
+      for (int u = 0; u < 4; ++u)
+        sts128(base + oDS + s * kTileS + swz((uint32_t)r, (uint32_t)(wg * 4 + u)), pk[4 * u], pk[4 * u + 1],
+               pk[4 * u + 2], pk[4 * u + 3]);
       fence_proxy_async_smem();
       mbar_arrive(bar(bDSfull + s));
     }
     mbar_wait(bar(bDone), 0);
     tcgen05_fence_after();
-    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(p.dq) + (((int64_t)b * p.S + q_idx) * p.H + h) * D;
+    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(p.dq) + (((int64_t)b * p.S + q_idx) * p.H + h) * D + wg * 64;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < 2; ++ch) {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(t_lane + (uint32_t)(256 + ch * 32), o);
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(256 + wg * 64 + ch * 32), o);
       tmem_ld_wait();
       if (live) {
 #pragma unroll
@@ -526,16 +617,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // backward: dK, dV  (key-stationary; 64-query steps)
 // =============================================================================================
 namespace bk {
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                        // as attn_bwd_dq: two warpgroups split the step's 64 query columns
 constexpr int BN = 64;                               // queries per step
 constexpr uint32_t kTileK = BM * D * 2;              // 32 KB
 constexpr uint32_t kChunkK = BM * 128;               // 16 KB
 constexpr uint32_t kTileQ = BN * D * 2;              // 16 KB (2 chunks of 8 KB)
 constexpr uint32_t kChunkQ = BN * 128;               // 8 KB
 constexpr uint32_t kTileS = BM * BN * 2;             // 16 KB: P^T / dS^T [128 keys][64 q]
-constexpr uint32_t oK = 0, oV = kTileK, oQ = 2 * kTileK, oDO = oQ + 2 * kTileQ, oPT = oDO + 2 * kTileQ,
+constexpr int QS = 3;                                // Q / dO ring depth (held until dV / dK of the step retire)
+constexpr uint32_t oK = 0, oV = kTileK, oQ = 2 * kTileK, oDO = oQ + QS * kTileQ, oPT = oDO + QS * kTileQ,
                    oDST = oPT + 2 * kTileS, oStat = oDST + 2 * kTileS, oBar = oStat + 2 * 2 * BN * 4;
-enum { bKV = 0, bQfull = 1, bQempty = 3, bSPfull = 5, bSPfree = 7, bPfull = 9, bPfree = 11, bDone = 13, nBars = 14 };
+enum { bKV = 0, bQfull = 1, bQempty = bQfull + QS, bSPfull = bQempty + QS, bSPfree = bSPfull + 2, bPfull = bSPfree + 2,
+       bPfree = bPfull + 2, bDone = bPfree + 2, nBars = bDone + 1 };
 constexpr uint32_t oTmem = oBar + 8 * nBars;
 constexpr uint32_t kSmem = oTmem + 16 + 1024;
 static_assert(kSmem <= 232448, "smem");
@@ -564,12 +657,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     prefetch_tensormap(&map_v);
     prefetch_tensormap(&map_do);
     mbar_init(bar(bKV), 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < QS; ++s) {
       mbar_init(bar(bQfull + s), 1);
       mbar_init(bar(bQempty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar(bSPfull + s), 1);
-      mbar_init(bar(bSPfree + s), 128);
-      mbar_init(bar(bPfull + s), 128);
+      mbar_init(bar(bSPfree + s), 256);
+      mbar_init(bar(bPfull + s), 256);
       mbar_init(bar(bPfree + s), 1);
     }
     mbar_init(bar(bDone), 1);
@@ -592,8 +687,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tma_load_3d(base + oV, &map_v, bar(bKV), col, k0, b);
       tma_load_3d(base + oV + kChunkK, &map_v, bar(bKV), col + 64, k0, b);
       for (int i = 0; i < n_steps; ++i) {
-        const int s = i & 1;
-        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        const int s = i % QS;
+        const uint32_t ph = (uint32_t)((i / QS) & 1);
         mbar_wait(bar(bQempty + s), ph ^ 1u);
         mbar_expect_tx(bar(bQfull + s), 2 * kTileQ);
         const int32_t qr = q_begin + i * BN;
@@ -608,19 +703,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);      // S^T / dP^T: M128 (keys) N64 (queries)
       constexpr uint32_t idesc_acc = make_idesc_bf16(BM, D, 0, 1);     // dV / dK: M128 N128, B MN-major
       auto issue_sp = [&](int i) {
-        const int s = i & 1;
+        const int s = i & 1, qs = i % QS;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
-        mbar_wait(bar(bQfull + s), ph);
+        mbar_wait(bar(bQfull + qs), (uint32_t)((i / QS) & 1));
         mbar_wait(bar(bSPfree + s), ph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_s = tmem + (uint32_t)(s * 128), d_p = d_s + 64u;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_f16<1>(d_s, desc_k_step(base + oK, kChunkK, k), desc_k_step(base + oQ + s * kTileQ, kChunkQ, k),
+          umma_f16<1>(d_s, desc_k_step(base + oK, kChunkK, k), desc_k_step(base + oQ + qs * kTileQ, kChunkQ, k),
                       idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_f16<1>(d_p, desc_k_step(base + oV, kChunkK, k), desc_k_step(base + oDO + s * kTileQ, kChunkQ, k),
+          umma_f16<1>(d_p, desc_k_step(base + oV, kChunkK, k), desc_k_step(base + oDO + qs * kTileQ, kChunkQ, k),
                       idesc_s, k > 0 ? 1u : 0u);
         umma_commit(bar(bSPfull + s));
       };
@@ -628,69 +723,72 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       issue_sp(0);
       for (int i = 0; i < n_steps; ++i) {
         if (i + 1 < n_steps) issue_sp(i + 1);
-        const int s = i & 1;
+        const int s = i & 1, qs = i % QS;
         mbar_wait(bar(bPfull + s), (uint32_t)((i >> 1) & 1));
         tcgen05_fence_after();
         const uint32_t d_k = tmem + 256u, d_v = tmem + 384u;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)
           umma_f16<1>(d_v, make_smem_desc(base + oPT + s * kTileS + (uint32_t)k * 32u),
-                      desc_mn_step(base + oDO + s * kTileQ, kChunkQ, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                      desc_mn_step(base + oDO + qs * kTileQ, kChunkQ, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)
           umma_f16<1>(d_k, make_smem_desc(base + oDST + s * kTileS + (uint32_t)k * 32u),
-                      desc_mn_step(base + oQ + s * kTileQ, kChunkQ, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar(bQempty + s));
+                      desc_mn_step(base + oQ + qs * kTileQ, kChunkQ, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar(bQempty + qs));
         umma_commit(bar(bPfree + s));
       }
       umma_commit(bar(bDone));
     }
   } else {
+    const int wg = (warp - 2) >> 2;                   // which half of the step's query columns
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                   // key row
-    const int st = threadIdx.x - 64;                  // 0..127 among the softmax threads
+    const int st = threadIdx.x - 64;                  // 0..255 among the softmax threads
     const int k_idx = k0 + r;
     const bool live = k_idx < p.S;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const float c = p.scale * kLog2e;
     const int64_t stat0 = ((int64_t)b * p.H + h) * p.S;
+    const int c0 = wg * 32;
     for (int i = 0; i < n_steps; ++i) {
       const int s = i & 1;
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
       const int qr = q_begin + i * BN;
-      // stage this step's 64 LSE (x log2 e) and 64 delta values: thread t < 64 -> lse, t >= 64 -> delta
+      // stage this step's 64 LSE (x log2 e) and 64 delta values: thread t < 64 -> lse, 64 <= t < 128 -> delta
       float* stat = reinterpret_cast<float*>(base_ptr + oStat) + s * 2 * BN;
-      {
+      if (st < 128) {
         const int qi = qr + (st & 63);
         float v = 0.f;
         if (qi < p.S) v = (st < 64) ? p.lse[stat0 + qi] * kLog2e : p.delta[stat0 + qi];
         stat[st] = v;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(bar(bSPfull + s), ph);
       tcgen05_fence_after();
-      uint32_t sv[64], dp[64];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + ch * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
-        tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + 64 + ch * 32), *reinterpret_cast<uint32_t(*)[32]>(&dp[ch * 32]));
-      }
+      uint32_t sv[32], dp[32];
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + c0), sv);
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + 64 + c0), dp);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(bar(bSPfree + s));
-      uint32_t ppk[32], dpk[32];
+      const bool edge = (p.causal && k0 + BM - 1 > qr) || (qr + BN > p.S) || (k0 + BM > p.S);
+      uint32_t ppk[16], dpk[16];
 #pragma unroll
-      for (int q = 0; q < 64; q += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(stat + q);
-        const float4 d4 = *reinterpret_cast<const float4*>(stat + BN + q);
+      for (int q = 0; q < 32; q += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(stat + c0 + q);
+        const float4 d4 = *reinterpret_cast<const float4*>(stat + BN + c0 + q);
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
         const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
         float pr[4], ds[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int q_idx = qr + q + e;
-          const bool dead = !live || q_idx >= p.S || (p.causal && k_idx > q_idx);
           const float pv = ex2f(fmaf(__uint_as_float(sv[q + e]), c, -ls[e]));
+          bool dead = false;
+          if (edge) {
+            const int q_idx = qr + c0 + q + e;
+            dead = !live || q_idx >= p.S || (p.causal && k_idx > q_idx);
+          }
           pr[e] = dead ? 0.f : pv;
           ds[e] = dead ? 0.f : pv * (__uint_as_float(dp[q + e]) - dl[e]) * p.scale;
         }
@@ -701,36 +799,34 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       mbar_wait(bar(bPfree + s), ph ^ 1u);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        sts128(base + oPT + s * kTileS + swz((uint32_t)r, (uint32_t)u), ppk[4 * u], ppk[4 * u + 1], ppk[4 * u + 2],
-               ppk[4 * u + 3]);
-        sts128(base + oDST + s * kTileS + swz((uint32_t)r, (uint32_t)u), dpk[4 * u], dpk[4 * u + 1], dpk[4 * u + 2],
-               dpk[4 * u + 3]);
+      for (int u = 0; u < 4; ++u) {
+        sts128(base + oPT + s * kTileS + swz((uint32_t)r, (uint32_t)(wg * 4 + u)), ppk[4 * u], ppk[4 * u + 1],
+               ppk[4 * u + 2], ppk[4 * u + 3]);
+        sts128(base + oDST + s * kTileS + swz((uint32_t)r, (uint32_t)(wg * 4 + u)), dpk[4 * u], dpk[4 * u + 1],
+               dpk[4 * u + 2], dpk[4 * u + 3]);
       }
       fence_proxy_async_smem();
       mbar_arrive(bar(bPfull + s));
     }
     mbar_wait(bar(bDone), 0);
     tcgen05_fence_after();
+    // warpgroup 0 stores dK, warpgroup 1 stores dV
     const int64_t off = (((int64_t)b * p.S + k_idx) * p.H + h) * D;
+    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(wg == 0 ? p.dk : p.dv) + off;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.dk : p.dv) + off;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(t_lane + (uint32_t)(256 + which * 128 + ch * 32), o);
-        tmem_ld_wait();
-        if (live) {
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_lane + (uint32_t)(256 + wg * 128 + ch * 32), o);
+      tmem_ld_wait();
+      if (live) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1]));
-            v.y = pack_bf16x2(__uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
-            v.z = pack_bf16x2(__uint_as_float(o[i + 4]), __uint_as_float(o[i + 5]));
-            v.w = pack_bf16x2(__uint_as_float(o[i + 6]), __uint_as_float(o[i + 7]));
-            *reinterpret_cast<uint4*>(row + ch * 32 + i) = v;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1]));
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]), __uint_as_float(o[i + 5]));
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]), __uint_as_float(o[i + 7]));
+          *reinterpret_cast<uint4*>(row + ch * 32 + i) = v;
         }
       }
     }
@@ -790,6 +886,11 @@ int check_common(const void* q, const void* k, const void* v, int B, int S, int 
 }  // namespace
 }  // namespace qat
 
+extern "C" int qat_attn_debug_trace(long long* dev_buffer) {   // 3 * 16 * 8 int64 slots, or NULL to switch off
+  qat::g_attn_trace = dev_buffer;
+  return QAT_OK;
+}
+
 extern "C" int qat_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
                             int head_dim, float softmax_scale, int causal, void* stream) {
   using namespace qat;
@@ -803,6 +904,7 @@ extern "C" int qat_attn_fwd(const void* q, const void* k, const void* v, void* o
   static bool flags[64] = {};
   if ((rc = set_smem(attn_fwd_kernel, fwd::kSmem, flags)) != QAT_OK) return rc;
   AttnParams p{};
+  p.trace = g_attn_trace;
   p.o = o;
   p.lse = lse;
   p.B = B;
