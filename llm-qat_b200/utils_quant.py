@@ -467,36 +467,49 @@ class _QuantLinearFn(torch.autograd.Function):
         # MN-major A) with the STE pass-mask applied to the fp32 accumulator in the epilogue.
         # fp32 modules keep the library GEMM + mask kernel.
         own = dtype == torch.bfloat16 and N % 8 == 0 and K % 8 == 0 and g2.data_ptr() % 16 == 0
+        # ... and, unless QAT_B200_BWD_DEQUANT_PASS=1, straight from the int8 codes: converter warps inside the
+        # GEMM rebuild the fake-quantized bf16 tiles in shared memory (no dequantized tensor in HBM)
+        from_codes = own and K % 16 == 0 and os.environ.get("QAT_B200_BWD_DEQUANT_PASS", "0") != "1"
         gx = gw = None
         with _on(dev):
             stream = _stream_ptr(dev)
             if ctx.needs_input_grad[0]:
-                wq = torch.empty((N, K), dtype=dtype, device=dev)           # == the reference's fake-quant W
-                check(L.qat_dequant_codes(wb, wb + we, wq.data_ptr(), N, K, dt, stream), "qat_dequant_codes")
-                if own:
+                if from_codes:
                     gx = torch.empty((T, K), dtype=dtype, device=dev)
-                    check(L.qat_gemm_bf16(g2.data_ptr(), wq.data_ptr(), gx.data_ptr(), xb + xm, T, K, N, 0, 1,
-                                          dt, 0, stream), "qat_gemm_bf16 (dgrad)")
+                    check(L.qat_gemm_bf16_codes(g2.data_ptr(), wb, wb + we, gx.data_ptr(), xb + xm, T, K, N, 0, dt, 0,
+                                                stream), "qat_gemm_bf16_codes (dgrad)")
                 else:
-                    t = torch.mm(g2, wq)
-                    gx = torch.empty_like(t)
-                    check(L.qat_ste_bwd_from_mask(t.data_ptr(), xb + xm, gx.data_ptr(), T * K, dt, stream),
-                          "qat_ste_bwd_from_mask")
-                del wq
+                    wq = torch.empty((N, K), dtype=dtype, device=dev)       # == the reference's fake-quant W
+                    check(L.qat_dequant_codes(wb, wb + we, wq.data_ptr(), N, K, dt, stream), "qat_dequant_codes")
+                    if own:
+                        gx = torch.empty((T, K), dtype=dtype, device=dev)
+                        check(L.qat_gemm_bf16(g2.data_ptr(), wq.data_ptr(), gx.data_ptr(), xb + xm, T, K, N, 0, 1,
+                                              dt, 0, stream), "qat_gemm_bf16 (dgrad)")
+                    else:
+                        t = torch.mm(g2, wq)
+                        gx = torch.empty_like(t)
+                        check(L.qat_ste_bwd_from_mask(t.data_ptr(), xb + xm, gx.data_ptr(), T * K, dt, stream),
+                              "qat_ste_bwd_from_mask")
+                    del wq
                 gx = gx.view(ctx.in_shape)
             if ctx.needs_input_grad[1]:
-                xq = torch.empty((T, K), dtype=dtype, device=dev)           # == the reference's fake-quant x
-                check(L.qat_dequant_codes(xb, xb + xe, xq.data_ptr(), T, K, dt, stream), "qat_dequant_codes")
-                if own:
+                if from_codes:
                     gw = torch.empty((N, K), dtype=dtype, device=dev)
-                    check(L.qat_gemm_bf16(g2.data_ptr(), xq.data_ptr(), gw.data_ptr(), wb + wm, N, K, T, 1, 1,
-                                          dt, 0, stream), "qat_gemm_bf16 (wgrad)")
+                    check(L.qat_gemm_bf16_codes(g2.data_ptr(), xb, xb + xe, gw.data_ptr(), wb + wm, N, K, T, 1, dt, 0,
+                                                stream), "qat_gemm_bf16_codes (wgrad)")
                 else:
-                    t = torch.mm(g2.t(), xq)
-                    gw = torch.empty_like(t)
-                    check(L.qat_ste_bwd_from_mask(t.data_ptr(), wb + wm, gw.data_ptr(), N * K, dt, stream),
-                          "qat_ste_bwd_from_mask")
-                del xq
+                    xq = torch.empty((T, K), dtype=dtype, device=dev)       # == the reference's fake-quant x
+                    check(L.qat_dequant_codes(xb, xb + xe, xq.data_ptr(), T, K, dt, stream), "qat_dequant_codes")
+                    if own:
+                        gw = torch.empty((N, K), dtype=dtype, device=dev)
+                        check(L.qat_gemm_bf16(g2.data_ptr(), xq.data_ptr(), gw.data_ptr(), wb + wm, N, K, T, 1, 1,
+                                              dt, 0, stream), "qat_gemm_bf16 (wgrad)")
+                    else:
+                        t = torch.mm(g2.t(), xq)
+                        gw = torch.empty_like(t)
+                        check(L.qat_ste_bwd_from_mask(t.data_ptr(), wb + wm, gw.data_ptr(), N * K, dt, stream),
+                              "qat_ste_bwd_from_mask")
+                    del xq
         # mode 1 keeps a module's codes only from its forward to its backward (for the checkpoint
         # recompute in between): 1.125 B per weight element must not sit in HBM through the
         # optimizer step

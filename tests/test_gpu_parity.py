@@ -771,7 +771,7 @@ def test_quantize_linear_backward_runs_on_own_kernels(monkeypatch):
             torch.cuda.synchronize()
         res.append((x.grad, lin.weight.grad, _lib.launch_count() - n0, [e.key for e in prof.key_averages()]))
     (gx_r, gw_r, _, _), (gx, gw, launches, kernels) = res
-    assert launches == 4, launches                         # 2 operand rebuilds + 2 contractions
+    assert launches == 2, launches                         # the two contractions, operands rebuilt in-kernel
     assert not any("nvjet" in k or "gemm" in k.lower() and "qat" not in k for k in kernels
                    if "gemm_bf16_kernel" not in k), kernels
     for a, c in ((gx_r, gx), (gw_r, gw)):
@@ -1033,3 +1033,37 @@ def test_qkv_prep_equals_kv_fake_quant_then_rope(amp, kv_bits):
     assert torch.equal(v1.grad, v2.grad)
     assert rel(q1.grad, q2.grad) <= 6e-3 and rel(k1.grad, k2.grad) <= 6e-3, (rel(q1.grad, q2.grad), rel(k1.grad, k2.grad))
     assert bool(((k1.grad == 0) == (k2.grad == 0)).float().mean() > 0.999)
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("shape", [(256, 256, 128), (304, 528, 200), (2048, 1024, 1088)])
+@pytest.mark.parametrize("amp", [False, True])
+def test_gemm_from_codes_is_bit_identical_to_dequant_then_gemm(a_mn, cg, shape, amp):
+    """qat_gemm_bf16_codes rebuilds B = fl_bf16(codes / e[row]) inside the kernel: its output must equal, bit
+    for bit, qat_dequant_codes followed by qat_gemm_bf16 on that tensor (same operands, same MMA order)."""
+    from llm_qat_b200 import _lib
+    from llm_qat_b200._lib import CODES_I8
+    from llm_qat_b200.utils_quant import dequant_codes, fake_quant_forward
+
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=gen).bfloat16().cuda()
+    a = A.t().contiguous() if a_mn else A
+    src = (torch.randn(K, N, generator=gen) * 0.7).bfloat16().cuda()     # rows = contraction index
+    _, codes, _, e, mask_src = fake_quant_forward(src, 4, False, True, want_y=False, codes_kind=CODES_I8, want_scales=True,
+                                                  mask_clip=(-2.0, 2.0), amp=amp)
+    bits = torch.rand(M * N, generator=gen) < 0.8
+    mask = _pack_bits(bits).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    L = _lib.lib()
+    out1 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.qat_gemm_bf16_codes(a.data_ptr(), codes.data_ptr(), e.data_ptr(), out1.data_ptr(), mask.data_ptr(), M, N, K,
+                                     a_mn, 1, cg, st), "qat_gemm_bf16_codes")
+    bq = dequant_codes(codes, e, torch.bfloat16)
+    out2 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.qat_gemm_bf16(a.data_ptr(), bq.data_ptr(), out2.data_ptr(), mask.data_ptr(), M, N, K, a_mn, 1, 1, cg, st),
+               "qat_gemm_bf16")
+    assert torch.equal(out1, out2), (shape, a_mn, cg, float((out1.float() - out2.float()).abs().max()))
+    ref = (A.float() @ bq.float()) * bits.view(M, N).cuda()
+    assert ((out1.float() - ref).norm() / ref.norm()).item() <= 4e-3
