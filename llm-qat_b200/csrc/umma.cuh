@@ -258,7 +258,13 @@ using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, voi
                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                               CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT on a thread that has not
+// touched the runtime yet (autograd's backward thread, when a tensor-map encode is the first CUDA call it
+// makes).  cudaFree(0) binds the device's primary context to the calling thread; ~100 ns once bound.
+inline void bind_context() { (void)cudaFree(nullptr); }
+
 inline EncodeFn get_encode() {
+  bind_context();
   static EncodeFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {

@@ -467,9 +467,12 @@ class _QuantLinearFn(torch.autograd.Function):
         # MN-major A) with the STE pass-mask applied to the fp32 accumulator in the epilogue.
         # fp32 modules keep the library GEMM + mask kernel.
         own = dtype == torch.bfloat16 and N % 8 == 0 and K % 8 == 0 and g2.data_ptr() % 16 == 0
-        # ... and, unless QAT_B200_BWD_DEQUANT_PASS=1, straight from the int8 codes: converter warps inside the
-        # GEMM rebuild the fake-quantized bf16 tiles in shared memory (no dequantized tensor in HBM)
-        from_codes = own and K % 16 == 0 and os.environ.get("QAT_B200_BWD_DEQUANT_PASS", "0") != "1"
+        # The operands are rebuilt from the codes by one streaming pass each (qat_dequant_codes, 25 us for
+        # [11008, 4096]).  QAT_B200_BWD_DEQUANT_PASS=0 selects the variant that rebuilds them INSIDE the GEMM
+        # (converter warps, no dequantized tensor in HBM): bit-identical, but measured 2.1-2.5x slower at
+        # T = 2048 (336 vs 133 + 25 us for dgrad [2048 x 11008] x [11008 x 4096]) — every weight tile is converted
+        # T / 256 times instead of once and the converters, not the tensor pipe, pace the k-loop.
+        from_codes = own and K % 16 == 0 and os.environ.get("QAT_B200_BWD_DEQUANT_PASS", "1") == "0"
         gx = gw = None
         with _on(dev):
             stream = _stream_ptr(dev)

@@ -752,6 +752,7 @@ def test_quantize_linear_backward_runs_on_own_kernels(monkeypatch):
     from oracle import ref_module
 
     monkeypatch.setenv("QAT_B200_FUSED_LINEAR", "1")
+    monkeypatch.delenv("QAT_B200_BWD_DEQUANT_PASS", raising=False)
     gen = torch.Generator().manual_seed(9)
     T, K, N = 512, 1024, 1536
     x0 = (torch.randn(T, K, generator=gen) * 1.2).bfloat16().cuda()
@@ -771,7 +772,7 @@ def test_quantize_linear_backward_runs_on_own_kernels(monkeypatch):
             torch.cuda.synchronize()
         res.append((x.grad, lin.weight.grad, _lib.launch_count() - n0, [e.key for e in prof.key_averages()]))
     (gx_r, gw_r, _, _), (gx, gw, launches, kernels) = res
-    assert launches == 2, launches                         # the two contractions, operands rebuilt in-kernel
+    assert launches == 4, launches                         # 2 operand rebuilds + 2 contractions
     assert not any("nvjet" in k or "gemm" in k.lower() and "qat" not in k for k in kernels
                    if "gemm_bf16_kernel" not in k), kernels
     for a, c in ((gx_r, gx), (gw_r, gw)):
@@ -1067,3 +1068,29 @@ def test_gemm_from_codes_is_bit_identical_to_dequant_then_gemm(a_mn, cg, shape, 
     assert torch.equal(out1, out2), (shape, a_mn, cg, float((out1.float() - out2.float()).abs().max()))
     ref = (A.float() @ bq.float()) * bits.view(M, N).cuda()
     assert ((out1.float() - ref).norm() / ref.norm()).item() <= 4e-3
+
+
+def test_quantize_linear_backward_in_gemm_dequant_variant_is_bit_identical(monkeypatch):
+    """QAT_B200_BWD_DEQUANT_PASS=0: operands rebuilt inside the contraction (no dequantized tensor in HBM) — the
+    gradients equal the default path's bit for bit, in two launches instead of four."""
+    from llm_qat_b200 import QuantizeLinear, _lib
+
+    gen = torch.Generator().manual_seed(13)
+    T, K, N = 384, 512, 768
+    x0 = (torch.randn(T, K, generator=gen) * 1.2).bfloat16().cuda()
+    w0 = (torch.randn(N, K, generator=gen) * 0.02).bfloat16().cuda()
+    g0 = torch.randn(T, N, generator=gen).bfloat16().cuda()
+    res = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QAT_B200_BWD_DEQUANT_PASS", mode)
+        lin = QuantizeLinear(K, N, w_bits=4, a_bits=8).bfloat16().cuda()
+        with torch.no_grad():
+            lin.weight.copy_(w0)
+        x = x0.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = lin(x)
+        n0 = _lib.launch_count()
+        out.backward(g0)
+        res.append((x.grad, lin.weight.grad, _lib.launch_count() - n0))
+    assert res[0][2] == 4 and res[1][2] == 2, (res[0][2], res[1][2])
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
