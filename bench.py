@@ -736,6 +736,19 @@ def run_b200(args):
                              "LLaMA-7B dims, random init, student W4A8KV4") + " + frozen FP teacher, KD (KL batchmean), "
                             "grad checkpointing, AdamW, bf16 inside torch.autocast(bf16) as kd_trainer.py:106 does; "
                             "llm_qat_b200.fuse_model + fused KD loss" + (", DDP/NCCL all-reduce" if world > 1 else ""))
+            if world > 1 and (args.weight_shard or args.qat_model == "13b"):
+                # BASELINE configs[4]: weights fake-quantized by output-channel shard (each rank quantizes
+                # out/world channels of every QuantizeLinear) + all-gather of int8 codes / divisors / masks over
+                # NVLink, against the replicated variant above (every rank quantizes every channel locally)
+                from llm_qat_b200 import sharding as SH
+
+                SH.enable_weight_sharding()
+                try:
+                    qat["weight_sharded"] = qat_arm(llm_qat_b200.utils_quant, True, nst)
+                    qat["weight_sharded"]["what"] = (f"weights quantized by output-channel shard across {world} ranks, "
+                                                     "codes all-gathered (1.125 B per weight element over NVLink)")
+                finally:
+                    SH.disable_weight_sharding()
             if not args.no_comparators:
                 qat["quant_path_only"] = qat_arm(llm_qat_b200.utils_quant, False, max(3, nst // 2))
                 qat["reference_eager_gpu"] = qat_arm(RM, False, max(3, nst // 2))
@@ -842,6 +855,9 @@ def main():
     ap.add_argument("--no-comparators", action="store_true",
                     help="skip the reference-eager-GPU and quant-path-only arms of the QAT step")
     ap.add_argument("--bucket-cap-mb", type=int, default=None, help="DDP gradient bucket size of the QAT step")
+    ap.add_argument("--weight-shard", action="store_true",
+                    help="add the QAT-step arm with weights quantized by output-channel shard (default on for 13b)")
+    ap.add_argument("--only-qat-step", action="store_true", help="skip the headline kernel timing extras (tools)")
     ap.add_argument("--shape-sweep", action="store_true",
                     help="add per-shape / per-dtype / per-quantizer kernel timings (SURVEY.md 8d config 1)")
     ap.add_argument("--qat-model", default="7b", choices=["7b", "13b"],
