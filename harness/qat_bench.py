@@ -13,8 +13,17 @@ from . import llama_qat as H
 
 
 def _timed(fn, warmup, steps):
-    for _ in range(warmup):
+    import os
+    import sys
+    import time
+
+    verbose = bool(os.environ.get("BENCH_VERBOSE"))
+    for i in range(warmup):
+        t0 = time.perf_counter()
         fn()
+        if verbose:
+            torch.cuda.synchronize()
+            print(f"[rank {os.environ.get('RANK', '0')}] warm-up step {i}: {time.perf_counter() - t0:.2f} s", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     times = []
     for _ in range(steps):

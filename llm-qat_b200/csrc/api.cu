@@ -28,7 +28,22 @@ int cuda_fail(cudaError_t e, const char* what) {
 namespace {
 std::atomic<int> g_pdl{-1};  // -1: read QAT_B200_PDL on first use
 }
-bool pdl_enabled() {
+std::atomic<int> g_pdl_mask{-1};
+bool pdl_enabled(int family) {
+  int m = g_pdl_mask.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("QAT_B200_PDL_MASK");
+    // Default: programmatic launch for the streaming quantizer kernels only (fakequant.cu, ste.cu, lowbit.cu —
+    // bits 0, 1, 3).  With EVERY family early-launching, a fused LLaMA-13B decoder layer's fwd+bwd issued
+    // without host synchronisation stops making progress (tests/gpu_layer13b_debug.py: reproducible; gone as
+    // soon as any one of dequant / K4 / gemm_bf16 / producers launches in plain stream order, or with
+    // CUDA_LAUNCH_BLOCKING=1; the 7B shapes never showed it).  The chain of persistent one-CTA-per-SM tcgen05
+    // kernels interleaved with small early-launched kernels is what the failing runs have in common; the
+    // scheduler-level cause is not visible from here, so those families give up the ~1.5 us per launch.
+    m = e != nullptr ? (int)(strtoul(e, nullptr, 16) & 0x7fffffffu) : 0x0B;
+    g_pdl_mask.store(m, std::memory_order_relaxed);
+  }
+  if (!((m >> family) & 1)) return false;
   int v = g_pdl.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("QAT_B200_PDL");

@@ -26,6 +26,7 @@
 // each recomputing P from the saved LSE (7 GEMMs of 128x128x64-ish tiles instead of the
 // minimal 5; deterministic, and every accumulator fits TMEM double-buffered).
 // Tensor-bound: 4 S^2 D H B / 2 flops forward (causal), x3.5 backward.
+#define QAT_PDL_FAMILY 6   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <cmath>
 #include <cstdlib>
 

@@ -5,6 +5,7 @@
 // saturate.  QuantizeLinear's backward uses it for the dgrad/wgrad operands, so
 // the forward can save 1 B/elem of codes instead of the reference's two
 // dequantized tensors.  HBM-bound: 1 + sizeof(T) bytes per element.
+#define QAT_PDL_FAMILY 2   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <type_traits>
 
 #include "common.cuh"

@@ -11,6 +11,7 @@
 //
 // HBM-bound: algorithmic traffic = 2*sizeof(T) bytes per element (+1/8 B with
 // the mask, +1 or 2 B with codes).  See DESIGN.md section "K1/K2".
+#define QAT_PDL_FAMILY 0   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <cstdlib>
 
 #include "common.cuh"

@@ -19,6 +19,7 @@
 // with the next tile through a double-buffered accumulator; CG = 2 pairs the two CTAs
 // of a cluster on one 256x256 tile (tcgen05.mma.cta_group::2).
 // Tensor-bound: 2*M*N*K flops against the bf16 dense peak.
+#define QAT_PDL_FAMILY 5   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <cstdlib>
 
 #include "umma.cuh"
@@ -393,7 +394,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaSt
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled(QAT_PDL_FAMILY) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MODE, CG>, ma, mb, p);

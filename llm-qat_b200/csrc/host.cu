@@ -12,6 +12,7 @@
 // (tests/gpu_pcie_probe.py), 41 GB/s at this pipeline's 8 MB copy size.  Everything is ordered
 // after prior work on the caller's stream and the caller's stream waits for the
 // last D2H, so stream semantics are those of a single asynchronous call.
+#define QAT_PDL_FAMILY 9   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <cstdlib>
 #include <vector>
 

@@ -10,6 +10,7 @@
 //   backward: d loss / d student = (softmax(student) - softmax(teacher)) * grad / B, one read of both
 //             logits + one write, from the saved row statistics; `grad` is read from device memory.
 // HBM-bound: forward 2e B/elem, backward 3e B/elem (e = bytes per logit).
+#define QAT_PDL_FAMILY 8   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include "common.cuh"
 
 namespace qat {

@@ -13,6 +13,7 @@
 // within fp32 rounding), derives the scale and applies from registers: 2e B/elem.
 // Layerwise mode, very long or unaligned rows: two launches, a double-precision
 // sum merged with atomics, then a pass that re-reads w and applies (3e B/elem).
+#define QAT_PDL_FAMILY 3   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include "common.cuh"
 
 namespace qat {

@@ -9,6 +9,7 @@
 // the same tensor (same SymScale chain from common.cuh, same packing), so QuantizeLinear consumes them
 // as if it had quantized its input itself.  All HBM-bound, one CTA (256 threads) per token row, the row
 // held in registers between the reductions and the store.
+#define QAT_PDL_FAMILY 7   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include "common.cuh"
 
 namespace qat {

@@ -31,6 +31,7 @@
 //   * smem: CG1 4 x (16 KB A + 32 KB B), CG2 6 x (16 KB A + 16 KB B), plus
 //     column-scale staging = ~195 KB.
 // Tensor-bound: 2*T*N*K integer ops; see DESIGN.md "K4".
+#define QAT_PDL_FAMILY 4   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <cstdlib>
 
 #include "umma.cuh"
@@ -348,7 +349,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled(QAT_PDL_FAMILY) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, qlinear_i8_kernel<OUT_DT, CG>, ma, mb, p);

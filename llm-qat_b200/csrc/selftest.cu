@@ -9,6 +9,7 @@
 // counters[4..5] additionally sweep numerators down to the denormal boundary,
 // where div.rn leaves its fast path and bit-equality is NOT expected (and not
 // needed): reported for information only.
+#define QAT_PDL_FAMILY 10   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include "common.cuh"
 
 namespace qat {

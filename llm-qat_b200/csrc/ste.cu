@@ -5,6 +5,7 @@
 // (5 ATen kernels: clone + 2 bool-mask compares + 2 masked fills) with one
 // streaming pass: read g, read x (or a forward-emitted packed mask), write gx.
 // HBM-bound: 3*sizeof(T) B/elem from x, 2*sizeof(T) + 1/8 B/elem from a mask.
+#define QAT_PDL_FAMILY 1   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include "common.cuh"
 
 namespace qat {
