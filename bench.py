@@ -711,8 +711,8 @@ def run_b200(args):
                 return float(t.item())
 
             if rank == 0:   # configs[2]: one decoder layer fwd+bwd, seq 2048, inside autocast(bf16)
-                layer = {"workload": "configs[2]: LlamaDecoderLayer W4A8KV4 bf16, hidden_states [1, 2048, 4096], fwd + bwd, "
-                                     "inside torch.autocast(bf16)"}
+                layer = {"workload": f"configs[2]: LlamaDecoderLayer W{cfg7.w_bits}A{cfg7.a_bits}KV{cfg7.kv_bits} bf16, "
+                                     f"hidden_states [1, 2048, {cfg7.hidden_size}], fwd + bwd, inside torch.autocast(bf16)"}
                 for name, quant, fm in (("b200_fused_model", llm_qat_b200.utils_quant, True),
                                         ("b200_quant_path_only", llm_qat_b200.utils_quant, False),
                                         ("reference_eager_gpu", RM, False)):

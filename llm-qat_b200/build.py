@@ -4,9 +4,9 @@
 
 Objects go to llm-qat_b200/build/, the library to llm-qat_b200/lib/ (both
 git-ignored; the .so travels to the GPU box with the gpurun snapshot).
-cudart is linked statically so the library has no load-time dependency beyond
-libc/libstdc++; the driver API (cuTensorMapEncodeTiled) is resolved at run time
-through cudaGetDriverEntryPoint.
+cudart is linked dynamically (libcudart.so.12: the one PyTorch has already loaded in
+a Python process; an rpath to the toolkit's copy serves plain C hosts); the driver API
+(cuTensorMapEncodeTiled) is resolved at run time through cudaGetDriverEntryPoint.
 """
 from __future__ import annotations
 
@@ -92,7 +92,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    link = [cc, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
+    link = [cc, *ARCH, "-shared", "-cudart", "shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC",
+            "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
