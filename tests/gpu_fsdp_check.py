@@ -20,15 +20,16 @@ from harness import llama_qat as H
 import llm_qat_b200
 
 
-def run(mode_env, steps=5, orig_params=False):
+def run(mode_env, steps=5, orig_params=False, fused_model=False):
     for k, v in mode_env.items():
         os.environ[k] = v
     rank = dist.get_rank()
-    cfg = H.QatConfig(hidden_size=256, intermediate_size=688, num_attention_heads=4, num_hidden_layers=3,
+    # head_dim 128 so that fuse_model's attention kernel is eligible
+    cfg = H.QatConfig(hidden_size=256, intermediate_size=688, num_attention_heads=2, num_hidden_layers=3,
                       vocab_size=512, max_position_embeddings=128, w_bits=4, a_bits=8, kv_bits=4)
     torch.manual_seed(0)
-    model = H.CausalLM(cfg, llm_qat_b200.utils_quant).bfloat16().cuda()
-    teacher = H.build_teacher(cfg).bfloat16().cuda()
+    model = H.CausalLM(cfg, llm_qat_b200.utils_quant, fused=fused_model).bfloat16().cuda()
+    teacher = H.build_teacher(cfg, fused=fused_model).bfloat16().cuda()
     teacher.load_state_dict(model.state_dict())
     policy = functools.partial(transformer_auto_wrap_policy, transformer_layer_cls={H.DecoderLayer})
     model = FSDP(model, auto_wrap_policy=policy, device_id=torch.cuda.current_device(),
@@ -41,7 +42,8 @@ def run(mode_env, steps=5, orig_params=False):
     for step in range(steps):
         ids = torch.randint(0, cfg.vocab_size, (2, 64), generator=g).cuda()
         model.train()
-        losses.append(float(H.qat_step(model, teacher, ids, opt)))
+        losses.append(float(H.qat_step(model, teacher, ids, opt, autocast=fused_model,
+                                       loss_fn=llm_qat_b200.fused_ops.kd_loss if fused_model else None)))
         if step == 2:   # an eval-style forward between steps: weights unchanged, caches may hit
             model.eval()
             with torch.no_grad():
@@ -66,6 +68,16 @@ def main():
             print(f"use_orig_params={orig}: caches off {['%.6f' % v for v in off]}  identical={same}")
             print(f"use_orig_params={orig}: unfused    {['%.6f' % v for v in unf]}  max rel diff vs fused {rel:.3e}")
             ok = ok and same and all(v == v for v in on)
+        # llm_qat_b200.fuse_model (attention / MLP / RMSNorm kernels, producer-emitted codes) under the same wrapper
+        f_on = run({"QAT_B200_CACHE": "1", "QAT_B200_FUSED_LINEAR": "1"}, orig_params=orig, fused_model=True)
+        f_off = run({"QAT_B200_CACHE": "0", "QAT_B200_FUSED_LINEAR": "1"}, orig_params=orig, fused_model=True)
+        if dist.get_rank() == 0:
+            same = f_on == f_off
+            rel = max(abs(a - b) / max(abs(b), 1e-9) for a, b in zip(f_on, on))
+            print(f"use_orig_params={orig}: fuse_model, caches on  {['%.6f' % v for v in f_on]}")
+            print(f"use_orig_params={orig}: fuse_model, caches off {['%.6f' % v for v in f_off]}  identical={same}  "
+                  f"max rel diff vs quant-path-only {rel:.3e}")
+            ok = ok and same and all(v == v for v in f_on) and rel < 0.1 and f_on[-1] < f_on[0]
     if dist.get_rank() == 0:
         print("FSDP CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.barrier()
