@@ -12,6 +12,16 @@ import torch
 from . import llama_qat as H
 
 
+def release_memory():
+    """DDP / autograd objects sit in reference cycles: without a collection the previous arm's 130 GB (13B)
+    is still allocated when the next arm builds its models."""
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
 def _timed(fn, warmup, steps):
     import os
     import sys
@@ -105,8 +115,8 @@ def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, 
     t = _timed(step, warmup, steps)
     ms = statistics.median(t)
     mem = torch.cuda.max_memory_allocated(device) / 2 ** 30
-    del opt, model, student, teacher
-    torch.cuda.empty_cache()
+    del opt, model, student, teacher, step
+    release_memory()
     return {"ms_per_step": round(ms, 2), "tokens_per_s_per_gpu": round(bsz * seq / ms * 1e3), "seq": seq,
             "bsz_per_gpu": bsz, "peak_mem_GiB": round(mem, 1), "layers": cfg.num_hidden_layers, "autocast": autocast,
             "fused_model": fused}
