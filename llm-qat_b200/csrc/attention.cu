@@ -11,10 +11,10 @@
 // Layout: Q, K, V, O, dO, dQ, dK, dV are bf16 [B, S, H, D] (the projections' own layout:
 // [b, s, hidden] viewed as heads — no transposes), D == 128.  LSE and delta are fp32 [B, H, S].
 //
-// Forward, one CTA per (128-query tile, head, batch), 320 threads:
-//   warp 0   TMA producer: Q once, K/V tiles of 128 keys through a 2-stage ring
-//   warp 1   MMA issuer:   S[b] = Q K_j^T  (M128 N128 K128, both K-major) issued two tiles ahead
-//                          O[b] += P_j V_j (A = P from shared memory, B = V MN-major),  b = j % 2
+// Forward, one CTA per (128-query tile, head, batch), 384 threads:
+//   warp 0 / 11 TMA producers: Q once and the K tiles / the V tiles (128 keys, 2-stage rings each)
+//   warp 1   MMA issuer:   S[b] = Q K_j^T  (M128 N128 K128, both K-major), up to two tiles ahead
+//   warp 10  MMA issuer:   O[b] += P_j V_j (A = P from shared memory, B = V MN-major),  b = j % 2
 //   warps 2-5, 6-9         two softmax warpgroups, tile parity b each: one thread per query row (a TMEM
 //                          lane): tcgen05.ld S, running max / sum in registers (no shuffles), P -> bf16 ->
 //                          128B-swizzled shared memory, lazy rescale of O[b] in TMEM (only when the row max
@@ -92,7 +92,8 @@ struct AttnParams {
 // partial results are merged once at the end (split-KV inside the CTA).  One thread per query
 // row: row max / sum never leave registers.
 namespace fwd {
-constexpr int kThreads = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-5 WG0, warps 6-9 WG1
+constexpr int kThreads = 384;                       // warp 0 TMA (Q, K), warp 1 QK^T issuer, warps 2-5 WG0, warps 6-9 WG1,
+                                                    // warp 10 PV issuer, warp 11 TMA (V)
 constexpr uint32_t kTile = BM * D * 2;              // 32 KB: [128][128] bf16 as 2 chunks of 16 KB
 constexpr uint32_t kChunk = BM * 128;               // 16 KB
 constexpr uint32_t oQ = 0, oK = kTile, oV = 3 * kTile, oP = 5 * kTile, oBar = 7 * kTile;
@@ -154,34 +155,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_expect_tx(bar(bQ), kTile);
       tma_load_3d(base + oQ, &map_q, bar(bQ), col, q0, b);
       tma_load_3d(base + oQ + kChunk, &map_q, bar(bQ), col + 64, q0, b);
-      // K_j is wanted two tiles ahead of V_j (Q K^T is issued two tiles early, P V only after the soft-max),
-      // and its stage frees as soon as Q K_{j-2}^T retires — so K loads run one tile ahead of the V loads
-      // instead of queueing behind a V stage that is still in use (measured: 1300 cycles of exposed TMA
-      // latency per tile with the K_j, V_j, K_{j+1}, V_{j+1} order; tests/gpu_attn_trace.py)
-      auto load_k = [&](int j) {
+      // K and V have their own producer threads (this one and warp 11): K_j is wanted two tiles ahead of V_j
+      // (Q K^T is issued two tiles early, P V only after the soft-max) and its stage frees as soon as
+      // Q K_{j-2}^T retires, whereas V's stage frees only after P V of tile j-2.  One in-order producer made
+      // the K loads queue behind V stages still in use: 1300-2600 cycles of exposed TMA latency per tile
+      // (tests/gpu_attn_trace.py).
+      for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         mbar_wait(bar(bKempty + s), (uint32_t)((j >> 1) & 1) ^ 1u);
         mbar_expect_tx(bar(bKfull + s), kTile);
         tma_load_3d(base + oK + s * kTile, &map_k, bar(bKfull + s), col, j * BM, b);
         tma_load_3d(base + oK + s * kTile + kChunk, &map_k, bar(bKfull + s), col + 64, j * BM, b);
-      };
-      auto load_v = [&](int j) {
+      }
+    }
+  } else if (warp == 11) {
+    if (lane == 0) {
+      const int32_t col = h * D;
+      for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         mbar_wait(bar(bVempty + s), (uint32_t)((j >> 1) & 1) ^ 1u);
         mbar_expect_tx(bar(bVfull + s), kTile);
         tma_load_3d(base + oV + s * kTile, &map_v, bar(bVfull + s), col, j * BM, b);
         tma_load_3d(base + oV + s * kTile + kChunk, &map_v, bar(bVfull + s), col + 64, j * BM, b);
-      };
-      load_k(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) load_k(j + 1);
-        load_v(j);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BM, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, 0, 1);
       // tile j uses K/V stage, S buffer, P buffer and O accumulator (j & 1); its use count is j >> 1
       auto issue_qk = [&](int j) {
         const int s = j & 1;
@@ -201,15 +201,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         umma_commit(bar(bSfull + s));
         trace(0, j, 3);
       };
+      // Q K^T and P V are issued by two different threads (this one and warp 10): each blocks only on its
+      // own barriers, so a late P_j never holds back Q K_{j+2}^T and a late K tile never holds back P V
+      // (one issuer spent ~500 of every 2000 cycles per tile in barrier round trips: tests/gpu_attn_trace.py)
       mbar_wait(bar(bQ), 0);
-      issue_qk(0);
-      if (n_kv > 1) issue_qk(1);
+      for (int j = 0; j < n_kv; ++j) issue_qk(j);
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, 0, 1);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        // S[s] is free as soon as its warpgroup has pulled tile j into registers: queue Q K_{j+2}^T now,
-        // so that it runs under that warpgroup's soft-max of tile j
-        if (j + 2 < n_kv) issue_qk(j + 2);
         trace(0, j, 4);
         mbar_wait(bar(bVfull + s), ph);
         trace(0, j, 5);
@@ -437,6 +440,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int kv_end = p.causal ? min(q0 + BM, p.S) : p.S;       // keys [0, kv_end)
   const int n_steps = (kv_end + BN - 1) / BN;
   auto bar = [&](int i) { return base + oBar + 8u * (uint32_t)i; };
+  // debug trace (qat_attn_debug_trace): slots [384, 768) of the buffer, role 0 = MMA thread, 1 / 2 = warpgroups
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto trace = [&](int role, int step, int ev) {
+    if (tracing && step < kTraceTiles) p.trace[384 + (role * kTraceTiles + step) * kTraceEvents + ev] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_q);
@@ -496,10 +504,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       auto issue_sp = [&](int j) {
         const int s = j & 1, ks = j % KS;
         const uint32_t ph = (uint32_t)((j >> 1) & 1), kph = (uint32_t)((j / KS) & 1);
+        trace(0, j, 0);
         mbar_wait(bar(bKfull + ks), kph);
         mbar_wait(bar(bVfull + ks), kph);
+        trace(0, j, 1);
         mbar_wait(bar(bSPfree + s), ph ^ 1u);
         tcgen05_fence_after();
+        trace(0, j, 2);
         const uint32_t d_s = tmem + (uint32_t)(s * 128), d_p = d_s + 64u;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
@@ -511,14 +522,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                       idesc_s, k > 0 ? 1u : 0u);
         umma_commit(bar(bVempty + ks));
         umma_commit(bar(bSPfull + s));
+        trace(0, j, 3);
       };
       mbar_wait(bar(bQ), 0);
       issue_sp(0);
       for (int j = 0; j < n_steps; ++j) {
         if (j + 1 < n_steps) issue_sp(j + 1);
         const int s = j & 1, ks = j % KS;
+        trace(0, j, 4);
         mbar_wait(bar(bDSfull + s), (uint32_t)((j >> 1) & 1));
         tcgen05_fence_after();
+        trace(0, j, 5);
         const uint32_t d_q = tmem + 256u;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)
@@ -526,6 +540,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                       desc_mn_step(base + oK + ks * kTileK, kChunkK, k), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar(bKempty + ks));
         umma_commit(bar(bDSfree + s));
+        trace(0, j, 6);
       }
       umma_commit(bar(bDone));
     }
@@ -541,17 +556,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const float lse_c = live ? p.lse[stat] * kLog2e : 0.f;
     const float dlt = live ? p.delta[stat] : 0.f;
     const int c0 = wg * 32;
+    const bool tr = (threadIdx.x == 64 || threadIdx.x == 192);
     for (int j = 0; j < n_steps; ++j) {
       const int s = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      if (tr) trace(1 + wg, j, 0);
       mbar_wait(bar(bSPfull + s), ph);
       tcgen05_fence_after();
+      if (tr) trace(1 + wg, j, 1);
       uint32_t sv[32], dp[32];
       tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + c0), sv);
       tmem_ld_32x32b_x32(t_lane + (uint32_t)(s * 128 + 64 + c0), dp);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(bar(bSPfree + s));
+      if (tr) trace(1 + wg, j, 2);
       const int k0 = j * BN + c0;
       const bool edge = (p.causal && j * BN + BN - 1 > q0) || (j * BN + BN > p.S) || (q0 + BM > p.S);
       uint32_t pk[16];
@@ -577,13 +596,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                                    p1 * (__uint_as_float(dp[i + 1]) - dlt) * p.scale);
         }
       }
+      if (tr) trace(1 + wg, j, 3);
       mbar_wait(bar(bDSfree + s), ph ^ 1u);        // the dQ MMA that read this dS buffer two steps ago is done
+      if (tr) trace(1 + wg, j, 4);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         sts128(base + oDS + s * kTileS + swz((uint32_t)r, (uint32_t)(wg * 4 + u)), pk[4 * u], pk[4 * u + 1],
                pk[4 * u + 2], pk[4 * u + 3]);
       fence_proxy_async_smem();
       mbar_arrive(bar(bDSfull + s));
+      if (tr) trace(1 + wg, j, 5);
     }
     mbar_wait(bar(bDone), 0);
     tcgen05_fence_after();
@@ -887,7 +909,7 @@ int check_common(const void* q, const void* k, const void* v, int B, int S, int 
 }  // namespace
 }  // namespace qat
 
-extern "C" int qat_attn_debug_trace(long long* dev_buffer) {   // 3 * 16 * 8 int64 slots, or NULL to switch off
+extern "C" int qat_attn_debug_trace(long long* dev_buffer) {   // 2 kernels x 3 roles x 16 steps x 8 events (int64), or NULL: off
   qat::g_attn_trace = dev_buffer;
   return QAT_OK;
 }
@@ -940,6 +962,7 @@ extern "C" int qat_attn_bwd(const void* q, const void* k, const void* v, const v
     QAT_CHECK_LAUNCH("attn_delta_kernel");
   }
   AttnParams p{};
+  p.trace = g_attn_trace;
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.dq = dq;
