@@ -368,8 +368,9 @@ class _QuantLinearFn(torch.autograd.Function):
               The weight's codes are kept on the module and reused by the
               gradient-checkpoint recompute of the same step (see QAT_B200_CACHE).
     backward: dequantized operands are rebuilt from codes (q / e, bit-identical
-              to the reference's fake-quant outputs); dgrad/wgrad are plain
-              library GEMMs; the STE masks saved by the forward gate them.
+              to the reference's fake-quant outputs); dgrad / wgrad run on this
+              library's tcgen05 bf16 GEMM, which reads them in place (MN-major) and
+              applies the STE masks saved by the forward in its epilogue.
     Saves 1 B/elem of codes + 1/8 B/elem of mask instead of the reference's two
     dequantized tensors plus two unquantized inputs.
     """
@@ -412,7 +413,9 @@ class _QuantLinearFn(torch.autograd.Function):
         we, wm, _ = _feed_layout(N, K)
         xb, wb = xblob.data_ptr(), wblob.data_ptr()
         if not reuse_w:
-            sh = _sharding.weight_sharding()
+            # never from inside a backward pass: a checkpoint recompute that missed the cache must not
+            # interleave a collective with DDP's gradient all-reduces (rank-dependent order -> deadlock)
+            sh = None if _in_backward_pass() else _sharding.weight_sharding()
             if sh is not None and _sharding.shardable(N, K, sh[1]):
                 # BASELINE configs[4]: this rank quantizes its out/world output channels, then the codes,
                 # divisors and masks (1.125 B/elem) are all-gathered over NVLink
