@@ -13,8 +13,12 @@ Metric: "fake-quant fwd+bwd GB/s" = algorithmic bytes of all ranks / max-over-ra
 device time.  Prints ONE JSON line (rank 0).  Extra objects on the same line:
 roofline (dominant kernel, live CUDA-event timing), cpu_baseline (torch-eager
 port of the reference on the host cores), e2e (host buffers through the C ABI's
-host entry points, H2D + D2H inside the timed region), qlinear (K4 tcgen05 GEMM),
-config1_fp32 (BASELINE configs[0] shapes), clocks.
+host entry points, H2D + D2H inside the timed region; link_probe = the host link's
+own ceiling with every rank copying at once), qlinear (K4 tcgen05 GEMM vs cuBLASLt
+int8 and vs the reference's eager QuantizeLinear.forward), config1_fp32 (BASELINE
+configs[0], each kernel with its roofline), config3_layer and qat_step (BASELINE
+configs[2] / [3] / [4]: this library with fuse_model vs the quant path only vs the
+reference's eager chain on the same GPU(s); 13b adds the output-channel-sharded arm), clocks.
 """
 from __future__ import annotations
 
@@ -865,7 +869,6 @@ def main():
     ap.add_argument("--bucket-cap-mb", type=int, default=None, help="DDP gradient bucket size of the QAT step")
     ap.add_argument("--weight-shard", action="store_true",
                     help="add the QAT-step arm with weights quantized by output-channel shard (default on for 13b)")
-    ap.add_argument("--only-qat-step", action="store_true", help="skip the headline kernel timing extras (tools)")
     ap.add_argument("--shape-sweep", action="store_true",
                     help="add per-shape / per-dtype / per-quantizer kernel timings (SURVEY.md 8d config 1)")
     ap.add_argument("--qat-model", default="7b", choices=["7b", "13b"],
