@@ -97,8 +97,11 @@ def time_qat_step(quant, cfg: H.QatConfig, seq=2048, bsz=1, warmup=3, steps=10, 
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
 
-        kw = {} if bucket_cap_mb is None else {"bucket_cap_mb": bucket_cap_mb}
-        model = DDP(student, device_ids=[torch.device(device).index], gradient_as_bucket_view=True, **kw)
+        # one gradient bucket per decoder layer (~400 MB of bf16 gradients) instead of 25 MB ones: 34 all-reduces per
+        # step instead of 540, less contention with the backward GEMMs; the model's only buffers are the rotary
+        # tables, identical on every rank by construction, so the per-forward buffer broadcast is switched off
+        model = DDP(student, device_ids=[torch.device(device).index], gradient_as_bucket_view=True,
+                    bucket_cap_mb=400 if bucket_cap_mb is None else bucket_cap_mb, broadcast_buffers=False)
     opt = torch.optim.AdamW(student.parameters(), lr=lr)
     g = torch.Generator().manual_seed(1234 + rank)
     ids = torch.randint(0, cfg.vocab_size, (bsz, seq), generator=g).to(device)

@@ -98,9 +98,9 @@ struct FeedOut {
 // ================================================================================================
 // RMSNorm (+ feed)
 // ================================================================================================
-constexpr int kRmsIters = 4;   // hidden <= 256 * 4 * 8 = 8192
+constexpr int kRmsMaxIters = 4;   // hidden <= 256 * 4 * 8 = 8192; kernels are instantiated for the exact count (registers)
 
-template <int DT>
+template <int DT, int kRmsIters>
 __global__ void __launch_bounds__(kThreads) rmsnorm_feed_kernel(const uint4* __restrict__ x,
                                                                 const uint4* __restrict__ w, uint4* __restrict__ y,
                                                                 float* __restrict__ rstd_out, int nvec, float eps,
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_feed_kernel(const uint4* __r
 
 // backward: gx = rstd * (g*w - xh * mean(g*w*xh)),  gw partial sums over this CTA's rows
 constexpr int kRmsBwdRows = 8;
+template <int kRmsIters>
 __global__ void __launch_bounds__(kThreads) rmsnorm_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x,
                                                                const uint4* __restrict__ w,
                                                                const float* __restrict__ rstd_in, uint4* __restrict__ gx,
@@ -243,11 +244,11 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
 // ================================================================================================
 // SiLU(gate) * up (+ feed)
 // ================================================================================================
-constexpr int kActIters = 8;   // intermediate <= 256 * 8 * 8 = 16384
+constexpr int kActMaxIters = 8;   // intermediate <= 256 * 8 * 8 = 16384
 
 __device__ __forceinline__ float silu_f(float xv) { return __fdividef(xv, 1.0f + __expf(-xv)); }
 
-template <int DT>
+template <int DT, int kActIters>
 __global__ void __launch_bounds__(kThreads) swiglu_feed_kernel(const uint4* __restrict__ gate,
                                                                const uint4* __restrict__ up, uint4* __restrict__ act,
                                                                int nvec, const FeedOut f) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) swiglu_bwd_kernel(const uint4* __res
 // One CTA per token: hidden = H * 128 <= 256 * 2 * 8 * ... each thread owns `kQkvIters` vectors of each
 // of q, k, v.  Vector j covers elements [8j, 8j+8) of the token's row; inside a head (128 = 16
 // vectors) the rotation partner of vector t is vector t ^ 8, i.e. thread (tid ^ 8) of the same warp.
-constexpr int kQkvIters = 4;   // hidden <= 8192
+constexpr int kQkvMaxIters = 4;   // hidden <= 8192
 
 template <int DT>
 __device__ __forceinline__ float rope_round(float v) { return DT == QAT_BF16 ? Num<QAT_BF16>::fl(v) : v; }
@@ -360,7 +361,7 @@ struct QkvParams {
   float lo, hi, qmax;
 };
 
-template <int DT>
+template <int DT, int kQkvIters>
 __global__ void __launch_bounds__(kThreads) qkv_prep_kernel(const QkvParams p) {
   __shared__ uint32_t sm_u[kThreads / 32];
   pdl_wait();
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(kThreads) qkv_prep_kernel(const QkvParams p) {
 // backward: dq = rope^T(dq_rot); dk = mask_k .* rope^T(dk_rot); dv = mask_v .* dv_q
 //   rope^T(dy)[d] = dy[d] cos[d] + dy[d+64] sin[d+64]   (d <  64)
 //                 = dy[d] cos[d] - dy[d-64] sin[d-64]   (d >= 64)
+template <int kQkvIters>
 __global__ void __launch_bounds__(kThreads) qkv_prep_bwd_kernel(const uint4* __restrict__ dq_rot,
                                                                 const uint4* __restrict__ dk_rot,
                                                                 const uint4* __restrict__ dv_q,
@@ -485,6 +487,22 @@ __global__ void __launch_bounds__(kThreads) qkv_prep_bwd_kernel(const uint4* __r
 
 float bf16_round_host(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// vectors per thread for a row of `nvec` 16-byte vectors: the kernels keep the row in registers, so they are
+// instantiated for the exact count (LLaMA-7B: 2 for hidden 4096, 6 for 11008) instead of the maximum
+inline int iters_for(int nvec) { return (nvec + kThreads - 1) / kThreads; }
+
+#define QAT_DISPATCH_ITERS(IT, MAXIT, CALL)                 \
+  switch (IT) {                                             \
+    case 1: { constexpr int I = 1; CALL; } break;            \
+    case 2: { constexpr int I = 2; CALL; } break;            \
+    case 3: { constexpr int I = 3; CALL; } break;            \
+    case 4: { constexpr int I = 4; CALL; } break;            \
+    case 5: { constexpr int I = (MAXIT) >= 5 ? 5 : 4; CALL; } break; \
+    case 6: { constexpr int I = (MAXIT) >= 6 ? 6 : 4; CALL; } break; \
+    case 7: { constexpr int I = (MAXIT) >= 7 ? 7 : 4; CALL; } break; \
+    default: { constexpr int I = (MAXIT) >= 8 ? 8 : 4; CALL; } break; \
+  }
+
 int check_feed(int dtype, int bits, int64_t cols, int max_cols) {
   QAT_CHECK_ARG(dtype == QAT_BF16 || dtype == QAT_BF16_AMP, "dtype must be QAT_BF16 or QAT_BF16_AMP (got %d)", dtype);
   QAT_CHECK_ARG(bits >= 2 && bits <= 8, "int8 feed needs 2 <= bits <= 8 (got %d)", bits);
@@ -511,7 +529,7 @@ extern "C" int qat_rmsnorm_feed_fwd(const void* x, const void* weight, void* y, 
                                     float* row_e, uint8_t* mask, float clip_lo, float clip_hi, int64_t rows,
                                     int64_t cols, float eps, int dtype, int bits, void* stream) {
   using namespace qat;
-  int rc = check_feed(dtype, codes ? bits : 8, cols, kThreads * kRmsIters * 8);
+  int rc = check_feed(dtype, codes ? bits : 8, cols, kThreads * kRmsMaxIters * 8);
   if (rc != QAT_OK) return rc;
   QAT_CHECK_ARG(rows >= 0, "negative rows");
   if (rows == 0) return QAT_OK;
@@ -523,13 +541,18 @@ extern "C" int qat_rmsnorm_feed_fwd(const void* x, const void* weight, void* y, 
   const FeedOut f = make_feed(codes, row_e, mask, clip_lo, clip_hi, bits);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nvec = (int)(cols / 8);
-  cudaError_t e;
-  if (dtype == QAT_BF16)
-    e = launch_pdl(rmsnorm_feed_kernel<QAT_BF16>, dim3((unsigned)rows), dim3(kThreads), 0, st,
-                   (const uint4*)x, (const uint4*)weight, (uint4*)y, rstd, nvec, eps, 1.0f / (float)cols, f);
-  else
-    e = launch_pdl(rmsnorm_feed_kernel<QAT_BF16_AMP>, dim3((unsigned)rows), dim3(kThreads), 0, st,
-                   (const uint4*)x, (const uint4*)weight, (uint4*)y, rstd, nvec, eps, 1.0f / (float)cols, f);
+  cudaError_t e = cudaSuccess;
+  if (dtype == QAT_BF16) {
+    QAT_DISPATCH_ITERS(iters_for(nvec), kRmsMaxIters,
+                       e = launch_pdl(rmsnorm_feed_kernel<QAT_BF16, I>, dim3((unsigned)rows), dim3(kThreads), 0, st,
+                                      (const uint4*)x, (const uint4*)weight, (uint4*)y, rstd, nvec, eps,
+                                      1.0f / (float)cols, f));
+  } else {
+    QAT_DISPATCH_ITERS(iters_for(nvec), kRmsMaxIters,
+                       e = launch_pdl(rmsnorm_feed_kernel<QAT_BF16_AMP, I>, dim3((unsigned)rows), dim3(kThreads), 0, st,
+                                      (const uint4*)x, (const uint4*)weight, (uint4*)y, rstd, nvec, eps,
+                                      1.0f / (float)cols, f));
+  }
   if (e != cudaSuccess) return cuda_fail(e, "rmsnorm_feed_kernel launch");
   QAT_CHECK_LAUNCH("rmsnorm_feed_kernel");
   return QAT_OK;
@@ -544,7 +567,7 @@ extern "C" int qat_rmsnorm_bwd(const void* grad_y, const void* x, const void* we
                                void* grad_weight, void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols,
                                void* stream) {
   using namespace qat;
-  QAT_CHECK_ARG(cols > 0 && cols % 8 == 0 && cols <= kThreads * kRmsIters * 8, "unsupported cols %lld", (long long)cols);
+  QAT_CHECK_ARG(cols > 0 && cols % 8 == 0 && cols <= kThreads * kRmsMaxIters * 8, "unsupported cols %lld", (long long)cols);
   QAT_CHECK_ARG(rows >= 0, "negative rows");
   if (rows == 0) return QAT_OK;
   QAT_CHECK_ARG(grad_y && x && weight && rstd && grad_x && grad_weight && workspace, "NULL operand");
@@ -553,9 +576,11 @@ extern "C" int qat_rmsnorm_bwd(const void* grad_y, const void* x, const void* we
                 "operands must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nblk = (int)((rows + kRmsBwdRows - 1) / kRmsBwdRows);
-  cudaError_t e = launch_pdl(rmsnorm_bwd_kernel, dim3((unsigned)nblk), dim3(kThreads), 0, st, (const uint4*)grad_y,
-                             (const uint4*)x, (const uint4*)weight, rstd, (uint4*)grad_x, (float*)workspace, rows,
-                             (int)(cols / 8), 1.0f / (float)cols);
+  cudaError_t e = cudaSuccess;
+  QAT_DISPATCH_ITERS(iters_for((int)(cols / 8)), kRmsMaxIters,
+                     e = launch_pdl(rmsnorm_bwd_kernel<I>, dim3((unsigned)nblk), dim3(kThreads), 0, st,
+                                    (const uint4*)grad_y, (const uint4*)x, (const uint4*)weight, rstd, (uint4*)grad_x,
+                                    (float*)workspace, rows, (int)(cols / 8), 1.0f / (float)cols));
   if (e != cudaSuccess) return cuda_fail(e, "rmsnorm_bwd_kernel launch");
   QAT_CHECK_LAUNCH("rmsnorm_bwd_kernel");
   e = launch_pdl(colsum_kernel, dim3((unsigned)((cols + kThreads - 1) / kThreads)), dim3(kThreads), 0, st,
@@ -569,7 +594,7 @@ extern "C" int qat_swiglu_feed_fwd(const void* gate, const void* up, void* act, 
                                    uint8_t* mask, float clip_lo, float clip_hi, int64_t rows, int64_t cols, int dtype,
                                    int bits, void* stream) {
   using namespace qat;
-  int rc = check_feed(dtype, codes ? bits : 8, cols, kThreads * kActIters * 8);
+  int rc = check_feed(dtype, codes ? bits : 8, cols, kThreads * kActMaxIters * 8);
   if (rc != QAT_OK) return rc;
   QAT_CHECK_ARG(rows >= 0, "negative rows");
   if (rows == 0) return QAT_OK;
@@ -581,13 +606,16 @@ extern "C" int qat_swiglu_feed_fwd(const void* gate, const void* up, void* act, 
   const FeedOut f = make_feed(codes, row_e, mask, clip_lo, clip_hi, bits);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nvec = (int)(cols / 8);
-  cudaError_t e;
-  if (dtype == QAT_BF16)
-    e = launch_pdl(swiglu_feed_kernel<QAT_BF16>, dim3((unsigned)rows), dim3(kThreads), 0, st, (const uint4*)gate,
-                   (const uint4*)up, (uint4*)act, nvec, f);
-  else
-    e = launch_pdl(swiglu_feed_kernel<QAT_BF16_AMP>, dim3((unsigned)rows), dim3(kThreads), 0, st, (const uint4*)gate,
-                   (const uint4*)up, (uint4*)act, nvec, f);
+  cudaError_t e = cudaSuccess;
+  if (dtype == QAT_BF16) {
+    QAT_DISPATCH_ITERS(iters_for(nvec), kActMaxIters,
+                       e = launch_pdl(swiglu_feed_kernel<QAT_BF16, I>, dim3((unsigned)rows), dim3(kThreads), 0, st,
+                                      (const uint4*)gate, (const uint4*)up, (uint4*)act, nvec, f));
+  } else {
+    QAT_DISPATCH_ITERS(iters_for(nvec), kActMaxIters,
+                       e = launch_pdl(swiglu_feed_kernel<QAT_BF16_AMP, I>, dim3((unsigned)rows), dim3(kThreads), 0, st,
+                                      (const uint4*)gate, (const uint4*)up, (uint4*)act, nvec, f));
+  }
   if (e != cudaSuccess) return cuda_fail(e, "swiglu_feed_kernel launch");
   QAT_CHECK_LAUNCH("swiglu_feed_kernel");
   return QAT_OK;
@@ -620,7 +648,7 @@ extern "C" int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, voi
   using namespace qat;
   QAT_CHECK_ARG(dtype == QAT_BF16 || dtype == QAT_BF16_AMP, "dtype must be QAT_BF16 or QAT_BF16_AMP (got %d)", dtype);
   QAT_CHECK_ARG(head_dim == 128, "head_dim must be 128 (got %d)", head_dim);
-  QAT_CHECK_ARG(heads > 0 && heads * 16 <= kThreads * kQkvIters, "unsupported head count %d", heads);
+  QAT_CHECK_ARG(heads > 0 && heads * 16 <= kThreads * kQkvMaxIters, "unsupported head count %d", heads);
   QAT_CHECK_ARG(kv_bits >= 2, "kv_bits must be >= 2 (got %d)", kv_bits);
   QAT_CHECK_ARG(tokens >= 0, "negative token count");
   if (tokens == 0) return QAT_OK;
@@ -646,9 +674,14 @@ extern "C" int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, voi
   p.hi = bf16_round_host(clip_hi);
   p.qmax = kv_bits < 32 ? (float)((1ll << (kv_bits - 1)) - 1) : 0.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e;
-  if (dtype == QAT_BF16) e = launch_pdl(qkv_prep_kernel<QAT_BF16>, dim3((unsigned)tokens), dim3(kThreads), 0, st, p);
-  else e = launch_pdl(qkv_prep_kernel<QAT_BF16_AMP>, dim3((unsigned)tokens), dim3(kThreads), 0, st, p);
+  cudaError_t e = cudaSuccess;
+  if (dtype == QAT_BF16) {
+    QAT_DISPATCH_ITERS(iters_for(p.nvec), kQkvMaxIters,
+                       e = launch_pdl(qkv_prep_kernel<QAT_BF16, I>, dim3((unsigned)tokens), dim3(kThreads), 0, st, p));
+  } else {
+    QAT_DISPATCH_ITERS(iters_for(p.nvec), kQkvMaxIters,
+                       e = launch_pdl(qkv_prep_kernel<QAT_BF16_AMP, I>, dim3((unsigned)tokens), dim3(kThreads), 0, st, p));
+  }
   if (e != cudaSuccess) return cuda_fail(e, "qkv_prep_kernel launch");
   QAT_CHECK_LAUNCH("qkv_prep_kernel");
   return QAT_OK;
@@ -660,15 +693,17 @@ extern "C" int qat_qkv_prep_bwd(const void* dq_rot, const void* dk_rot, const vo
                                 int head_dim, void* stream) {
   using namespace qat;
   QAT_CHECK_ARG(head_dim == 128, "head_dim must be 128 (got %d)", head_dim);
-  QAT_CHECK_ARG(heads > 0 && heads * 16 <= kThreads * kQkvIters, "unsupported head count %d", heads);
+  QAT_CHECK_ARG(heads > 0 && heads * 16 <= kThreads * kQkvMaxIters, "unsupported head count %d", heads);
   if (tokens <= 0) return QAT_OK;
   QAT_CHECK_ARG(dq_rot && dk_rot && dv_q && dq && dk && dv && cos_table && sin_table && position_ids, "NULL operand");
   QAT_CHECK_ARG((((uintptr_t)dq_rot | (uintptr_t)dk_rot | (uintptr_t)dv_q | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
                 "operands must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = launch_pdl(qkv_prep_bwd_kernel, dim3((unsigned)tokens), dim3(kThreads), 0, st, (const uint4*)dq_rot,
-                             (const uint4*)dk_rot, (const uint4*)dv_q, k_mask, v_mask, cos_table, sin_table,
-                             position_ids, (uint4*)dq, (uint4*)dk, (uint4*)dv, heads * 16);
+  cudaError_t e = cudaSuccess;
+  QAT_DISPATCH_ITERS(iters_for(heads * 16), kQkvMaxIters,
+                     e = launch_pdl(qkv_prep_bwd_kernel<I>, dim3((unsigned)tokens), dim3(kThreads), 0, st,
+                                    (const uint4*)dq_rot, (const uint4*)dk_rot, (const uint4*)dv_q, k_mask, v_mask,
+                                    cos_table, sin_table, position_ids, (uint4*)dq, (uint4*)dk, (uint4*)dv, heads * 16));
   if (e != cudaSuccess) return cuda_fail(e, "qkv_prep_bwd_kernel launch");
   QAT_CHECK_LAUNCH("qkv_prep_bwd_kernel");
   return QAT_OK;
