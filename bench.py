@@ -55,25 +55,26 @@ def bench_config(world: int):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-# `ncu --set full` capture (profiles/): filled in from profiles/r01_ncu_summary.json
+# `ncu --set full` capture (profiles/): filled in from profiles/rNN_ncu_summary.json
+def _ncu_summary():
+    for tag in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.json")) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return {}
+
+
 def _load_ncu_traffic():
-    path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
-    try:
-        with open(path) as f:
-            return {k: v.get("dram_bytes_per_launch") for k, v in json.load(f).get("kernels", {}).items()}
-    except Exception:
-        return {}
+    return {k: v.get("dram_bytes_per_launch") for k, v in _ncu_summary().get("kernels", {}).items()}
 
 
 NCU_TRAFFIC = _load_ncu_traffic()
 
 
 def _load_ncu_gemm():
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
-            return json.load(f).get("kernels", {}).get("qlinear_i8", {})
-    except Exception:
-        return {}
+    return _ncu_summary().get("kernels", {}).get("qlinear_i8", {})
 
 
 NCU_GEMM = _load_ncu_gemm()
