@@ -189,3 +189,24 @@ int main(void) {
                     "-L", lib_dir, "-l:libqat_b200.so", "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "abi ok 100" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_pdl_is_switched_off_while_a_torch_profiler_is_active():
+    """Programmatic dependent launch x CUPTI: the binding turns PDL off for the duration of a torch.profiler
+    session (the stall it avoids is reproduced by tests/gpu_pdl_profiler_soak.py)."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+
+    from llm_qat_b200 import _lib
+
+    if not _lib._pdl_auto:
+        import pytest
+
+        pytest.skip("QAT_B200_PDL is forced or off in this environment")
+    _lib.lib()
+    assert _lib._pdl_suppressed is False or _lib._INJECTED
+    with profile(activities=[ProfilerActivity.CPU]):
+        _lib.lib()
+        assert _lib._pdl_suppressed is True
+    _lib.lib()
+    assert _lib._pdl_suppressed is _lib._INJECTED
