@@ -517,3 +517,39 @@ def test_fused_model_layer_vs_live_reference_golden():
     assert max(base.values()) <= 5e-3, base
     for k, v in errs.items():
         assert v <= 1.5 * grid[k] + 1e-2, (k, v, grid[k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["7b", "13b"])
+def test_fused_layer_is_bit_deterministic_over_back_to_back_iterations(model):
+    """Race check for the tcgen05 pipelines (compute-sanitizer is closed on this pool): no kernel of the fused
+    layer uses atomics, so 24 forward+backward passes issued back to back WITHOUT host synchronisation (kernels
+    of consecutive iterations overlap at their edges) must give bit-identical outputs and gradients — at the
+    LLaMA-7B and the LLaMA-13B shapes (the latter is where a launch-overlap stall was found and fixed)."""
+    import llm_qat_b200
+
+    cfg = (H.QatConfig.llama_13b(w_bits=4, a_bits=8, kv_bits=8) if model == "13b"
+           else H.QatConfig.llama_7b(w_bits=4, a_bits=8, kv_bits=4))
+    torch.manual_seed(0)
+    layer = H.DecoderLayer(cfg, llm_qat_b200.utils_quant).bfloat16().cuda()
+    llm_qat_b200.fuse_model(layer)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 2048, cfg.hidden_size, generator=g).bfloat16().cuda().requires_grad_(True)
+    go = torch.randn(1, 2048, cfg.hidden_size, generator=g).bfloat16().cuda()
+    mask = llm_qat_b200.mark_causal_mask(H.causal_mask(1, 2048, torch.bfloat16, "cuda"))
+    pos = torch.arange(2048, device="cuda")[None]
+    runs = []
+    for _ in range(24):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = layer(x, mask, pos)
+        y.backward(go)
+        runs.append((y.detach(), x.grad.clone(), layer.mlp.up_proj.weight.grad.clone(),
+                     layer.self_attn.k_proj.weight.grad.clone(), layer.input_layernorm.weight.grad.clone()))
+        x.grad = None
+        for p in layer.parameters():
+            p.grad = None
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(t).all() for t in runs[0])
+    for i, r in enumerate(runs[1:], 1):
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b), (model, i, float((a.float() - b.float()).abs().max()))
