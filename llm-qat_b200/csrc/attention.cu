@@ -25,7 +25,8 @@
 //   attn_bwd_dkv  (key-stationary, 64-query steps):  S^T, dP^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
 // each recomputing P from the saved LSE (7 GEMMs of 128x128x64-ish tiles instead of the
 // minimal 5; deterministic, and every accumulator fits TMEM double-buffered).
-// Tensor-bound: 4 S^2 D H B / 2 flops forward (causal), x3.5 backward.
+// 4 S^2 D H B / 2 flops forward (causal), x3.5 backward; measured limits (tests/gpu_attn_trace.py): the exponentials
+// (MUFU, 16 ex2 per clock) in the forward, shared-memory operand bandwidth of the N = 64 MMAs in the backward.
 #define QAT_PDL_FAMILY 6   // bit of QAT_B200_PDL_MASK (common.cuh)
 #include <cmath>
 #include <cstdlib>

@@ -36,7 +36,6 @@ constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BLOCK_N;   // 512
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiThreads = 128;
 constexpr int kEpiWarps = 4;
 constexpr uint32_t kChunkBytes = 64 * BLOCK_K * 2;   // one MN-major TMA box: 64 K-rows x 128 B = 8 KB
 
