@@ -73,6 +73,11 @@ def _rope_tables(self, seq_len: int, device):
     return tabs
 
 
+def _on_gpu(t: torch.Tensor) -> bool:
+    """The fused kernels exist for CUDA tensors only (tests substitute CPU emulations and patch this)."""
+    return t.is_cuda
+
+
 def _module_clip(self):
     """(lo, hi) of act_clip_val_k, read once per tensor version: a clip tensor that lives on the GPU (a model
     built under `with torch.device("cuda")`) would otherwise cost a device-to-host sync in every forward."""
@@ -91,7 +96,7 @@ def _attention_forward(self, hidden_states, attention_mask=None, position_ids=No
                        output_attentions=False, use_cache=False):
     orig = self._qat_orig_forward
     if (past_key_value is not None or output_attentions or position_ids is None or self.head_dim != 128
-            or not hidden_states.is_cuda or not _is_causal(attention_mask)):
+            or not _on_gpu(hidden_states) or not _is_causal(attention_mask)):
         return orig(hidden_states, attention_mask, position_ids, past_key_value, output_attentions, use_cache)
     bsz, q_len, _ = hidden_states.size()
     cos, sin = _rope_tables(self, q_len, hidden_states.device)
@@ -109,7 +114,7 @@ def _attention_forward(self, hidden_states, attention_mask=None, position_ids=No
     qr, kr, vq = F.qkv_prep(q, k, v, cos, sin, pos, self.num_heads, kv_bits, clip)
     shape = (bsz, q_len, self.num_heads, self.head_dim)
     o = F.causal_attention(qr.view(shape), kr.view(shape), vq.view(shape), causal=True)
-    out = self.o_proj(o.view(bsz, q_len, self.hidden_size))
+    out = self.o_proj(o.reshape(bsz, q_len, self.hidden_size))
     present = (kr.view(shape).transpose(1, 2), vq.view(shape).transpose(1, 2)) if use_cache else None
     return out, None, present
 

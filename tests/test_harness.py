@@ -553,3 +553,95 @@ def test_fused_layer_is_bit_deterministic_over_back_to_back_iterations(model):
     for i, r in enumerate(runs[1:], 1):
         for a, b in zip(runs[0], r):
             assert torch.equal(a, b), (model, i, float((a.float() - b.float()).abs().max()))
+
+
+@needs_reference
+def test_fuse_model_glue_on_the_real_model_file_with_emulated_kernels():
+    """The patched forwards (llm-qat_b200/model_patch.py) driven through the UNMODIFIED reference
+    LlamaForCausalLM on the CPU, with the four fused ops replaced by eager restatements of the reference's own
+    formulas: logits, cache tensors and gradients must equal the original forward's — i.e. the glue (mask
+    recognition inside LlamaModel.forward, position ids, RoPE tables taken from LlamaRotaryEmbedding, kv_bits,
+    clip values, output tuple, use_cache) is right against the real model file, not only the harness."""
+    import subprocess
+
+    code = r'''
+import sys, math
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, %r)
+import torch
+import models
+from oracle import ref_module as R
+sys.modules["models.utils_quant"] = R; models.utils_quant = R      # CPU-capable quantizers under the reference's name
+from models.configuration_llama import LlamaConfig
+from models import modeling_llama_quant as M
+import llm_qat_b200
+from llm_qat_b200 import model_patch as MP
+
+calls = {"attn": 0, "qkv": 0, "swiglu": 0, "rms": 0}
+def qkv_prep(q, k, v, cos, sin, pos, heads, kv_bits, clip):
+    calls["qkv"] += 1
+    b, s, hid = q.shape
+    c = torch.tensor(list(clip))
+    if kv_bits < 32:
+        k = R.SymQuantizer.apply(k, c, kv_bits, False); v = R.SymQuantizer.apply(v, c, kv_bits, False)
+    sh = (b, s, heads, hid // heads)
+    qh, kh = q.view(sh).transpose(1, 2), k.view(sh).transpose(1, 2)
+    cs, sn = cos.to(v.dtype)[pos].unsqueeze(1), sin.to(v.dtype)[pos].unsqueeze(1)
+    qe = (qh * cs) + (M.rotate_half(qh) * sn); ke = (kh * cs) + (M.rotate_half(kh) * sn)
+    return qe.transpose(1, 2).reshape(b, s, hid), ke.transpose(1, 2).reshape(b, s, hid), v
+def causal_attention(q, k, v, scale=None, causal=True):
+    calls["attn"] += 1
+    b, s, h, d = q.shape
+    qh, kh, vh = (t.transpose(1, 2) for t in (q, k, v))
+    w = torch.matmul(qh, kh.transpose(2, 3)) / math.sqrt(d)
+    m = torch.full((s, s), torch.finfo(w.dtype).min, dtype=w.dtype).triu(1)
+    w = torch.max(w + m[None, None], torch.tensor(torch.finfo(w.dtype).min))
+    w = torch.nn.functional.softmax(w, dim=-1, dtype=torch.float32).to(qh.dtype)
+    return torch.matmul(w, vh).transpose(1, 2)
+def swiglu(gate, up, feed_bits=0):
+    calls["swiglu"] += 1
+    return torch.nn.functional.silu(gate) * up
+def rmsnorm(x, w, eps, feed_bits=0):
+    calls["rms"] += 1
+    var = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+    return w * (x * torch.rsqrt(var + eps)).to(w.dtype)
+MP.F.qkv_prep, MP.F.causal_attention, MP.F.swiglu, MP.F.rmsnorm = qkv_prep, causal_attention, swiglu, rmsnorm
+MP.F.swiglu_supported = lambda g, u: True
+MP.F.rmsnorm_supported = lambda x, w: True
+MP._on_gpu = lambda t: True
+
+cfg = LlamaConfig(hidden_size=256, intermediate_size=688, num_attention_heads=2, num_hidden_layers=2, vocab_size=128,
+                  max_position_embeddings=64, w_bits=4, a_bits=8, kv_bits=4)
+cfg.kv_bits = 4
+torch.manual_seed(0)
+model = M.LlamaForCausalLM(cfg).bfloat16()
+ids = torch.randint(0, 128, (2, 24), generator=torch.Generator().manual_seed(1))
+def run(**kw):
+    model.zero_grad()
+    out = model(input_ids=ids, use_cache=True, **kw)
+    out.logits.float().sum().backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    return out.logits.detach(), out.past_key_values, grads
+l0, pkv0, g0 = run()
+llm_qat_b200.fuse_model(model)
+l1, pkv1, g1 = run()
+assert calls["attn"] == 2 and calls["qkv"] == 2 and calls["swiglu"] == 2 and calls["rms"] == 5, calls
+assert torch.equal(l0, l1), float((l0.float() - l1.float()).abs().max())
+for (k0, v0), (k1, v1) in zip(pkv0, pkv1):
+    assert k0.shape == k1.shape and torch.equal(k0, k1) and torch.equal(v0, v1)
+for n in g0:
+    assert torch.equal(g0[n], g1[n]), n
+# an explicit all-ones mask is still recognised as causal; a padded one takes the reference's own attention
+n_attn = calls["attn"]
+l2, _, _ = run(attention_mask=torch.ones(2, 24, dtype=torch.long))
+assert calls["attn"] == n_attn + 2 and torch.equal(l2, l0)
+pad = torch.ones(2, 24, dtype=torch.long); pad[0, :5] = 0
+model(input_ids=ids, attention_mask=pad)
+assert calls["attn"] == n_attn + 2
+llm_qat_b200.unfuse_model(model)
+l3, _, _ = run()
+assert torch.equal(l3, l0)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
