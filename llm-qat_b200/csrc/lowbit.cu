@@ -6,15 +6,20 @@
 //   forward value = (q - w) + w           (gradient is the identity)
 // The mean is per output row, or over the whole tensor when layerwise.
 //
-// Row-wise mode with rows that fit registers (every LLaMA weight): ONE pass, the
-// K1 structure — a thread group owns a row, loads it with 128-bit streaming
-// loads, sums |w| in double precision (the sum order of torch's vectorised CPU
-// reduction is not a portable contract; fp64 makes ours order-independent to
-// within fp32 rounding), derives the scale and applies from registers: 2e B/elem.
-// Layerwise mode, very long or unaligned rows: two launches, a double-precision
-// sum merged with atomics, then a pass that re-reads w and applies (3e B/elem).
+// Row-wise mode (and layerwise below 32768 elements): ONE pass, one CTA per row with the row staged in
+// shared memory, mean|w| summed in the exact order of torch's CPU reduction (torch_sum_order.cuh) so that
+// the scale — and every element scaled by it — carries the reference's bits in fp32 and bf16: 2e B/elem.
+// Larger layerwise tensors (torch splits that reduction over its threads: no portable bit contract) and
+// rows beyond one CTA's shared memory: two launches, a double-precision sum merged with atomics, then a
+// pass that re-reads w and applies (3e B/elem).
 #define QAT_PDL_FAMILY 3   // bit of QAT_B200_PDL_MASK (common.cuh)
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
+#include "torch_sum_order.cuh"
 
 namespace qat {
 namespace {
@@ -109,11 +114,13 @@ __device__ __forceinline__ uint32_t lowbit_pair_bf16(uint32_t w2, float sf, floa
   const float r0 = __fmul_rn(bf16lo(w2), rsf), r1 = __fmul_rn(bf16hi(w2), rsf);   // w / sf  (one multiply: "anyratio")
   uint32_t q2;
   if (w_bits == 1) {
-    const uint32_t rb = pack_bf16x2(r0, r1);   // fl_bf16 first: a quotient may round to zero
-    const float a = bf16lo(rb), b = bf16hi(rb);
-    const float s0 = (a > 0.f) ? sf : (a < 0.f) ? -sf : __fmul_rn(sf, 0.f);        // sf * sign(r); sign(NaN) = 0
-    const float s1 = (b > 0.f) ? sf : (b < 0.f) ? -sf : __fmul_rn(sf, 0.f);
-    q2 = pack_bf16x2(s0, s1);
+    // sf * sign(r) on the pair: sign = (r > 0) - (r < 0) as packed compares (1.0 / 0.0 each; NaN compares false,
+    // like torch.sign(NaN) = 0 here), fl_bf16 of the quotient first because it may round to zero
+    const uint32_t rb = pack_bf16x2(r0, r1);
+    const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rb);
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+    const __nv_bfloat162 sg = __hsub2(__hgt2(r2, zero), __hlt2(r2, zero));
+    q2 = mul_bf16x2(sf2, *reinterpret_cast<const uint32_t*>(&sg));                  // :211-213
   } else {
     const uint32_t k2 = 0x40004000u, kh = 0x3f003f00u, k192 = 0x43404340u;        // 2.0, 0.5, 192.0 as bf16x2
     uint32_t t2 = clamp_nan_bf16x2(pack_bf16x2(r0, r1), clip2 ^ 0x80008000u, clip2);  // :229-231
@@ -125,124 +132,169 @@ __device__ __forceinline__ uint32_t lowbit_pair_bf16(uint32_t w2, float sf, floa
   return add_bf16x2(sub_bf16x2(q2, w2), w2);                                      // :240-242  (q - w) + w
 }
 
-// one thread group (a power of two >= 32 threads) per row, ITERS 16-byte vectors per thread
-template <int DT, int ITERS>
-__global__ void __launch_bounds__(1024) lowbit_row_kernel(const void* __restrict__ w, void* __restrict__ out,
-                                                          int64_t rows, int64_t nvec, int64_t cols, int log2_group,
-                                                          int w_bits) {
+// One CTA per row, the row staged ONCE in shared memory (any width, any alignment): one HBM read, one HBM
+// write.  mean|w| follows torch's own summation order (torch_sum_order.cuh): the 32 chains of ATen's
+// vectorised cascade sum are the 32 lanes of a warp, the independent 16-step groups of a chain are spread over
+// the CTA's warps (phase A), warp 0 folds the group sums through the cascade levels (phase B) and thread 0 does
+// the final fold over vectors, tail and lanes — the bits of `w.abs().mean(dim=-1)` on the reference's CPU,
+// fp32 and bf16 alike.
+// VEC (both base pointers 16-byte aligned): global memory is touched in aligned 16-byte chunks whatever the row
+// pitch — a row that starts `off` bytes into a chunk is staged `off` bytes into the buffer, so chunk j of the
+// row's span is chunk j of shared memory, input and output rows have the same phase, and only the (at most two)
+// chunks a row shares with its neighbours are handled element by element.  !VEC: element accesses throughout.
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(512) lowbit_exact_kernel(const void* __restrict__ w, void* __restrict__ out,
+                                                           int64_t cols, int w_bits, uint32_t gs_offset) {
   using N = Num<DT>;
-  __shared__ double sm[32];
-  const uint32_t group = 1u << log2_group;
-  const uint32_t t = threadIdx.x & (group - 1u);
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> log2_group) + (threadIdx.x >> log2_group);
-  const bool row_ok = row < rows;
-  const uint32_t nv = row_ok ? (uint32_t)nvec : 0u;
-  const uint4* wrow = reinterpret_cast<const uint4*>(w) + row * nvec;
+  using Elem = typename std::conditional<DT == QAT_F32, float, uint16_t>::type;
+  constexpr int kPer = N::kPerVec;   // elements per 16-byte chunk
+  extern __shared__ uint4 smem16[];
+  float* gs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem16) + gs_offset);   // [groups][32]
+  const int64_t row = blockIdx.x;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const int64_t steps = tso::chain_steps(cols), groups = steps / tso::kGroup;
+  float* chain = gs + groups * tso::kChains;   // [32]
+  float* total = chain + tso::kChains;         // [1]
+  // the row's span in aligned chunks (VEC); element e of the row sits at srow[e] either way
+  const int64_t elem0 = row * cols;                                   // first element, counted from the base pointer
+  const uint32_t off = VEC ? (uint32_t)(elem0 % kPer) : 0u;           // elements into its first chunk
+  const int64_t chunk0 = VEC ? elem0 / kPer : 0;
+  const uint32_t nchunks = VEC ? (uint32_t)((off + cols + kPer - 1) / kPer) : 0u;
+  const uint32_t full_lo = off ? 1u : 0u;                             // chunks [full_lo, full_hi) belong to this row alone
+  const bool shared_last = VEC && ((off + cols) % kPer) != 0;
+  const uint32_t full_hi = shared_last ? nchunks - 1u : nchunks;
+  const int64_t head = off ? min((int64_t)(kPer - off), cols) : 0;    // elements of a shared first chunk
+  const int64_t tail0 = shared_last ? max(head, (int64_t)full_hi * kPer - off) : cols;   // first element of a shared last chunk
+  Elem* srow = reinterpret_cast<Elem*>(smem16) + off;
   pdl_wait();
   pdl_launch_dependents();
-  uint4 v[ITERS];
+  if constexpr (VEC) {
+    const uint4* src = reinterpret_cast<const uint4*>(w) + chunk0;
+    for (uint32_t j0 = full_lo + tid; j0 < full_hi; j0 += 4u * nthr) {   // four loads in flight per thread
+      uint4 r[4];
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const uint32_t j = t + (uint32_t)i * group;
-    v[i] = (j < nv) ? ldg_stream(wrow + j) : make_uint4(0u, 0u, 0u, 0u);
-  }
-  double acc = 0.0;
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = j0 + (uint32_t)u * nthr;
+        if (j < full_hi) r[u] = ldg_stream(src + j);
+      }
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    if (DT == QAT_BF16) {
-      // eight bf16 magnitudes summed in fp32 (exact unless their exponents spread over more than
-      // 2^13 — and then off by < 2^-24, below what torch's own fp32 accumulation loses), fp64 across
-      float part = 0.f;
-#pragma unroll
-      for (int k = 0; k < N::kPerVec; ++k) part += fabsf(vec_get<DT>(v[i], k));
-      acc += (double)part;
-    } else {
-#pragma unroll
-      for (int k = 0; k < N::kPerVec; ++k) acc += (double)fabsf(vec_get<DT>(v[i], k));
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = j0 + (uint32_t)u * nthr;
+        if (j < full_hi) smem16[j] = r[u];
+      }
     }
+    const Elem* srcE = reinterpret_cast<const Elem*>(w) + elem0;
+    if (tid < head) srow[tid] = srcE[tid];
+    if (tail0 + tid < cols) srow[tail0 + tid] = srcE[tail0 + tid];
+  } else {
+    const Elem* srcE = reinterpret_cast<const Elem*>(w) + elem0;
+    for (int64_t j = tid; j < cols; j += nthr) srow[j] = srcE[j];
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (group > 32) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) sm[warp] = acc;
+  __syncthreads();
+  auto mag = [srow](int64_t e) -> float {
+    if constexpr (DT == QAT_F32) return fabsf(srow[e]);
+    else return fabsf(bf16lo((uint32_t)srow[e]));
+  };
+  if (cols >= tso::kLanes) {
+    for (int64_t g = warp; g < groups; g += nwarps) gs[g * tso::kChains + lane] = tso::group_sum(mag, g, lane);
     __syncthreads();
-    const int nw = group >> 5;
-    const int base = (warp / nw) * nw;
-    double tsum = (lane < nw) ? sm[base + lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
-    acc = tsum;
+    if (warp == 0) {
+      chain[lane] = tso::chain_sum(mag, [gs, lane](int64_t g) { return gs[g * tso::kChains + lane]; }, steps, lane);
+      __syncwarp();
+      if (lane == 0) total[0] = tso::finalize(mag, [chain](int c) { return chain[c]; }, cols);
+    }
+  } else if (tid == 0) {
+    total[0] = tso::short_row_sum(mag, cols);
   }
-  const float mean_abs = N::fl((float)(acc / (double)cols));                 // :205-210 / :219-224
+  __syncthreads();
+  const float mean_abs = N::fl(__fdiv_rn(total[0], (float)cols));            // :205-210 / :219-224 (mean_out: sum / K)
   const float sf = (w_bits == 1) ? mean_abs : N::fl(__fmul_rn(2.0f, mean_abs));
   const float clip = N::fl(0.99f);  // 1 - 1e-2, cast to the tensor dtype by clamp (:218)
   const float rsf = (DT == QAT_BF16 && recip_range_ok(sf)) ? __frcp_rn(sf) : 0.f;
-  uint4* orow = reinterpret_cast<uint4*>(out) + row * nvec;
-  if constexpr (DT == QAT_BF16) {
-    if (rsf != 0.f) {   // row-uniform: the packed chain, from registers
-      const uint32_t sf2 = pack_bf16x2(sf, sf), clip2 = pack_bf16x2(clip, clip);
-#pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const uint32_t j = t + (uint32_t)i * group;
-        const uint4 o = make_uint4(lowbit_pair_bf16(v[i].x, sf, rsf, sf2, clip2, w_bits),
-                                   lowbit_pair_bf16(v[i].y, sf, rsf, sf2, clip2, w_bits),
-                                   lowbit_pair_bf16(v[i].z, sf, rsf, sf2, clip2, w_bits),
-                                   lowbit_pair_bf16(v[i].w, sf, rsf, sf2, clip2, w_bits));
-        if (j < nv) stg_stream(orow + j, o);
-      }
-    } else if (row_ok) {
-      // scale 0 / inf / NaN / outside the proven window (all-zero or overflowed rows): exact IEEE
-      // division, element by element straight from global memory — rare, and kept away from the
-      // register-resident path (the division's slow path is a subroutine call)
-      const uint16_t* wr = reinterpret_cast<const uint16_t*>(w) + row * cols;
-      __nv_bfloat16* outr = reinterpret_cast<__nv_bfloat16*>(out) + row * cols;
+  Elem* outE = reinterpret_cast<Elem*>(out) + elem0;
+  auto one = [&](int64_t c) {   // element c of the row, the scalar chain (exact division unless rsf allows the multiply)
+    if constexpr (DT == QAT_F32) {
+      outE[c] = lowbit_eff<DT>(srow[c], sf, 0.f, clip, w_bits);
+    } else {
+      const __nv_bfloat16 y = __float2bfloat16_rn(lowbit_eff<DT>(bf16lo((uint32_t)srow[c]), sf, rsf, clip, w_bits));
+      outE[c] = *reinterpret_cast<const uint16_t*>(&y);
+    }
+  };
+  if (!VEC || (DT == QAT_BF16 && rsf == 0.f)) {
+    // element accesses; also bf16 rows whose scale is 0 / inf / NaN / outside the proven window (all-zero or
+    // overflowed rows): exact IEEE division — rare, and kept out of the unrolled path (its slow path is a call)
 #pragma unroll 1
-      for (int64_t c = t; c < cols; c += group)
-        outr[c] = __float2bfloat16_rn(lowbit_eff<DT>(bf16lo(wr[c]), sf, 0.f, clip, w_bits));
+    for (int64_t c = tid; c < cols; c += nthr) one(c);
+    return;
+  }
+  if constexpr (VEC) {
+    uint4* dst = reinterpret_cast<uint4*>(out) + chunk0;
+    if constexpr (DT == QAT_BF16) {
+      const uint32_t sf2 = pack_bf16x2(sf, sf), clip2 = pack_bf16x2(clip, clip);
+      for (uint32_t j = full_lo + tid; j < full_hi; j += nthr) {   // the packed chain
+        const uint4 v = smem16[j];
+        stg_stream(dst + j, make_uint4(lowbit_pair_bf16(v.x, sf, rsf, sf2, clip2, w_bits),
+                                       lowbit_pair_bf16(v.y, sf, rsf, sf2, clip2, w_bits),
+                                       lowbit_pair_bf16(v.z, sf, rsf, sf2, clip2, w_bits),
+                                       lowbit_pair_bf16(v.w, sf, rsf, sf2, clip2, w_bits)));
+      }
+    } else {
+      for (uint32_t j = full_lo + tid; j < full_hi; j += nthr) {
+        const uint4 v = smem16[j];
+        stg_stream(dst + j, make_uint4(__float_as_uint(lowbit_eff<DT>(__uint_as_float(v.x), sf, 0.f, clip, w_bits)),
+                                       __float_as_uint(lowbit_eff<DT>(__uint_as_float(v.y), sf, 0.f, clip, w_bits)),
+                                       __float_as_uint(lowbit_eff<DT>(__uint_as_float(v.z), sf, 0.f, clip, w_bits)),
+                                       __float_as_uint(lowbit_eff<DT>(__uint_as_float(v.w), sf, 0.f, clip, w_bits))));
+      }
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const uint32_t j = t + (uint32_t)i * group;
-      float y[N::kPerVec];
-#pragma unroll
-      for (int k = 0; k < N::kPerVec; ++k) y[k] = lowbit_eff<DT>(vec_get<DT>(v[i], k), sf, rsf, clip, w_bits);
-      const uint4 o = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2 % N::kPerVec]),
-                                 __float_as_uint(y[3 % N::kPerVec]));
-      if (j < nv) stg_stream(orow + j, o);
-    }
+    if (tid < head) one(tid);
+    if (tail0 + tid < cols) one(tail0 + tid);
   }
 }
 
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+// shared memory of one CTA: the row (16-byte padded), the level-0 group sums, 32 chain sums, the total
+inline size_t exact_smem_bytes(int64_t cols, int elem_bytes, uint32_t* gs_offset) {
+  const size_t row_bytes = (((size_t)cols * elem_bytes + 15) & ~(size_t)15) + 16;   // + the row's phase within a chunk
+  const size_t groups = (size_t)(tso::chain_steps(cols) / tso::kGroup);
+  *gs_offset = (uint32_t)row_bytes;
+  return row_bytes + (groups * tso::kChains + tso::kChains + 4) * sizeof(float);
+}
+
+template <int DT, bool VEC>
+cudaError_t launch_exact_variant(const void* w, void* out, int64_t rows, int64_t cols, int w_bits, size_t smem,
+                                 uint32_t gs_offset, int threads, cudaStream_t st) {
+  static std::atomic<bool> raised{false};   // > 48 KB of dynamic shared memory is an opt-in, once per kernel
+  if (smem > 48 * 1024 && !raised.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(lowbit_exact_kernel<DT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kMaxDynSmem);
+    if (e != cudaSuccess) return e;
+    raised.store(true, std::memory_order_release);
+  }
+  return launch_pdl(lowbit_exact_kernel<DT, VEC>, dim3((unsigned)rows), dim3((unsigned)threads), smem, st, w, out, cols,
+                    w_bits, gs_offset);
+}
+
+// false: the row does not fit one CTA's shared memory (the caller falls back to the two-pass kernels)
 template <int DT>
-bool launch_row_kernel(const void* w, void* out, int64_t rows, int64_t cols, int w_bits, cudaStream_t st) {
-  const int per = 16 / Num<DT>::kBytes;
-  if (cols % per != 0 || ((uintptr_t)w & 15) != 0 || ((uintptr_t)out & 15) != 0) return false;
-  const int64_t nvec = cols / per;
-  int group = 32, lg = 5;
-  while (group < 1024 && (nvec + group - 1) / group > 8) {
-    group <<= 1;
-    ++lg;
+bool launch_exact(const void* w, void* out, int64_t rows, int64_t cols, int w_bits, cudaStream_t st, cudaError_t* err) {
+  const int eb = Num<DT>::kBytes;
+  uint32_t gs_offset = 0;
+  const size_t smem = exact_smem_bytes(cols, eb, &gs_offset);
+  if (smem > kMaxDynSmem || rows > 0x7fffffffLL || cols >= (1LL << 24)) return false;
+  // one round of four 16-byte loads per thread where the row allows it: a CTA's lifetime is what the last,
+  // partly filled wave of rows costs, so it is kept short rather than the CTA small
+  const int64_t chunks = ((int64_t)cols * eb + 15) / 16;
+  int threads = (int)std::min<int64_t>(512, std::max<int64_t>(128, ((chunks + 3) / 4 + 63) / 64 * 64));
+  if (const char* t = getenv("QAT_B200_LOWBIT_THREADS")) {   // tuning knob (tests/gpu_lowbit_probe.py)
+    const int v = atoi(t);
+    if (v >= 32 && v <= 512 && v % 32 == 0) threads = v;
   }
-  const int64_t iters = (nvec + group - 1) / group;
-  if (iters > 8) return false;
-  const int block = group < 256 ? 256 : group;
-  const int64_t grid64 = (rows + block / group - 1) / (block / group);
-  if (grid64 > 0x7fffffffLL) return false;
-  const dim3 g((unsigned)grid64), b((unsigned)block);
-#define QAT_LB(IT) (void)launch_pdl(lowbit_row_kernel<DT, IT>, g, b, 0, st, w, out, rows, nvec, cols, lg, w_bits)
-  switch ((int)iters) {
-    case 1: QAT_LB(1); break;
-    case 2: QAT_LB(2); break;
-    case 3: QAT_LB(3); break;
-    case 4: QAT_LB(4); break;
-    case 5: QAT_LB(5); break;
-    case 6: QAT_LB(6); break;
-    case 7: QAT_LB(7); break;
-    default: QAT_LB(8); break;
-  }
-#undef QAT_LB
+  const bool vec = ((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 15) == 0;
+  *err = vec ? launch_exact_variant<DT, true>(w, out, rows, cols, w_bits, smem, gs_offset, threads, st)
+             : launch_exact_variant<DT, false>(w, out, rows, cols, w_bits, smem, gs_offset, threads, st);
   return true;
 }
 
@@ -270,18 +322,26 @@ int qat_lowbit_weight_fwd(const void* w, void* w_eff, int64_t rows, int64_t cols
     set_error("low-bit weight path needs %zu bytes of workspace (got %zu)", need, workspace_bytes);
     return QAT_ERR_WORKSPACE;
   }
-  if (rows > 65535) {
-    set_error("low-bit weight path supports at most 65535 rows (got %lld)", (long long)rows);
-    return QAT_ERR_UNSUPPORTED;
-  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!layerwise) {   // one pass with the row in registers whenever the layout allows
-    const bool done = dtype == QAT_F32 ? launch_row_kernel<QAT_F32>(w, w_eff, rows, cols, w_bits, st)
-                                       : launch_row_kernel<QAT_BF16>(w, w_eff, rows, cols, w_bits, st);
+  // Per-row scales, and the layerwise scale of a tensor below 32768 elements (which torch reduces as ONE serial
+  // cascade over the flattened tensor): one pass, mean|w| in torch's own order.  A larger layerwise tensor is
+  // split over torch's intra-op threads — the reference's bits depend on its machine — and takes the
+  // order-independent double-precision sum below, like rows too long for one CTA's shared memory.
+  const bool flat = layerwise && rows * cols < 32768;
+  if (!layerwise || flat) {
+    const int64_t r = flat ? 1 : rows, c = flat ? rows * cols : cols;
+    cudaError_t le = cudaSuccess;
+    const bool done = dtype == QAT_F32 ? launch_exact<QAT_F32>(w, w_eff, r, c, w_bits, st, &le)
+                                       : launch_exact<QAT_BF16>(w, w_eff, r, c, w_bits, st, &le);
     if (done) {
-      QAT_CHECK_LAUNCH("lowbit_row_kernel");
+      if (le != cudaSuccess) return cuda_fail(le, "lowbit_exact_kernel");
+      QAT_CHECK_LAUNCH("lowbit_exact_kernel");
       return QAT_OK;
     }
+  }
+  if (rows > 65535) {
+    set_error("low-bit weight path: two-pass kernels support at most 65535 rows (got %lld)", (long long)rows);
+    return QAT_ERR_UNSUPPORTED;
   }
   cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");

@@ -195,16 +195,80 @@ def pack_mask(mask: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------
 # QuantizeLinear low-bit weight path  (utils_quant.py:202-242)
 # --------------------------------------------------------------------------
+LAYERWISE_SPLIT_NUMEL = 32768   # at::internal::GRAIN_SIZE: full reductions from this size on are thread-split
+
+
+def _cascade(load, n: int):
+    """ATen's ``multi_row_sum`` (aten/src/ATen/native/cpu/SumKernel.cpp): n steps over independent chains, level 0
+    folded into level 1 after every 16 steps, 1 into 2 after every 256, 2 into 3 after every 4096."""
+    ceil_log2 = 0 if n <= 1 else int(n - 1).bit_length()
+    lp = max(4, ceil_log2 // 4)
+    step, mask = 1 << lp, (1 << lp) - 1
+    acc = [np.zeros_like(load(0)) for _ in range(4)]
+    i = 0
+    while i + step <= n:
+        for _ in range(step):
+            acc[0] = acc[0] + load(i)
+            i += 1
+        for j in range(1, 4):
+            acc[j] = acc[j] + acc[j - 1]
+            acc[j - 1] = np.zeros_like(acc[j - 1])
+            if i & (mask << (j * lp)):
+                break
+    while i < n:
+        acc[0] = acc[0] + load(i)
+        i += 1
+    for j in range(1, 4):
+        acc[0] = acc[0] + acc[j]
+    return acc[0]
+
+
+def torch_cpu_row_sum(a: np.ndarray) -> np.ndarray:
+    """``torch.sum(a, dim=-1)`` of a contiguous float32 [rows, cols] tensor on the CPU, bit for bit, as the AVX2
+    build of ATen computes it (``cascade_sum`` -> ``vectorized_inner_sum``: vectors of 8 lanes, 4 vectors per step,
+    a 4-level cascade per chain, left-over vectors, the fold over the 4 vectors, then tail and lanes in one scalar;
+    rows shorter than one vector take the same scheme on scalars).  The kernel-side twin is
+    llm-qat_b200/csrc/torch_sum_order.cuh; tests/test_torch_sum_order.py pins both to ``torch.sum`` itself.
+    A row is never split over threads as long as there is more than one row (or fewer than 32768 elements)."""
+    a = np.ascontiguousarray(a, dtype=F32)
+    rows, cols = a.shape
+    lanes = 8 if cols >= 8 else 1
+    nvec = cols // lanes
+    n = nvec // 4
+    with np.errstate(all="ignore"):
+        if n > 0:
+            p = _cascade(lambda i: a[:, i * 4 * lanes:(i + 1) * 4 * lanes], n).reshape(rows, 4, lanes)
+        else:
+            p = np.zeros((rows, 4, lanes), F32)
+        p0 = p[:, 0].copy()
+        for v in range(n * 4, nvec):
+            p0 = p0 + a[:, v * lanes:(v + 1) * lanes]
+        for k in range(1, 4):
+            p0 = p0 + p[:, k]
+        fin = np.zeros(rows, F32)
+        for e in range(nvec * lanes, cols):
+            fin = fin + a[:, e]
+        for lane in range(lanes):
+            fin = fin + p0[:, lane]
+    return fin
+
+
 def _mean_rows(a: np.ndarray, layerwise: bool, dtype: str) -> np.ndarray:
-    """torch.mean on CPU accumulates fp32 with a vectorised cascade sum whose
-    order depends on the host's SIMD width, so it is not a portable contract;
-    we accumulate in float64 and round once.  In bf16 the final rounding hides
-    the difference (bit-exact vs the live reference); in fp32 this statistic --
-    and everything scaled by it -- is compared at a few-ulp tolerance."""
+    """``a.mean(dim=-1, keepdim=True)`` (:205-210, :219-224) as torch's CPU kernels compute it: the fp32 row sum in
+    ATen's order (``torch_cpu_row_sum``), one true division by the column count, and for bf16 tensors a cast to
+    fp32 before and one rounding to bf16 after (ReduceOps.cpp ``mean_out``) — bit-exact in both dtypes.
+    Layerwise (``a.mean()`` of the whole tensor, unused by the model): below 32768 elements (at::internal::GRAIN_SIZE)
+    the same cascade runs over the flattened tensor — exact; from there on torch splits the reduction over its
+    intra-op threads, so the reference's own bits depend on the machine's thread count
+    (tests/test_torch_sum_order.py shows it): that statistic is accumulated in float64 here and compared at a
+    few-ulp tolerance in fp32."""
     fl = _fl(dtype)
-    if layerwise:
+    if layerwise and a.size >= LAYERWISE_SPLIT_NUMEL:
         return fl(np.asarray(np.mean(a.astype(np.float64)), dtype=F32).reshape(1, 1))
-    return fl(np.mean(a.astype(np.float64), axis=1, keepdims=True).astype(F32))
+    if layerwise:          # one serial cascade over the flattened tensor: exact
+        a = a.reshape(1, -1)
+    with np.errstate(all="ignore"):
+        return fl((torch_cpu_row_sum(a) / F32(a.shape[1])).astype(F32).reshape(-1, 1))
 
 
 def lowbit_weight(w: np.ndarray, w_bits: int, layerwise: bool = False, dtype: str = "fp32"):

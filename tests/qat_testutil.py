@@ -121,7 +121,8 @@ def lowbit_edge_cases():
     that pins the oracle to the live reference and the GPU test that pins the kernels to the oracle."""
     gen = torch.Generator().manual_seed(12)
     for dtype in ("fp32", "bf16"):
-        for rows, cols in ((64, 4096), (16, 11008), (9, 1000), (5, 172), (7, 1023)):
+        for rows, cols in ((64, 4096), (16, 11008), (9, 1000), (5, 172), (7, 1023), (5, 7), (5, 20), (6, 33),
+                           (5, 40000)):
             w = (torch.randn(rows, cols, generator=gen) * 0.02).to(DTYPES[dtype])
             w[0] = 0.0
             w[1, :6] = torch.tensor([float("inf"), -float("inf"), 1e-30, -1e-30, -0.0, 3.0]).to(w.dtype)
@@ -133,9 +134,17 @@ def lowbit_edge_cases():
                     yield dtype, w, bits, lw
 
 
-def lowbit_close(got: np.ndarray, ref: np.ndarray, dtype: str) -> bool:
-    """bf16: bit for bit.  fp32: same NaN / inf pattern and 2e-6 relative (mean|w| summation order)."""
-    if dtype == "bf16":
+def lowbit_exact(layerwise: bool, numel: int) -> bool:
+    """Where the W1 / W2 effective weight is a bit contract: always for per-row scales; for the layerwise scale only
+    below 32768 elements — from there on torch splits the full `mean()` over its threads and the reference's own
+    bits depend on the machine (tests/test_torch_sum_order.py)."""
+    return (not layerwise) or numel < 32768
+
+
+def lowbit_close(got: np.ndarray, ref: np.ndarray, dtype: str, exact: bool = True) -> bool:
+    """Bit for bit; with exact=False (large layerwise tensors, see lowbit_exact) bf16 stays bit for bit and fp32 is
+    the same NaN / inf pattern and 2e-6 relative (the thread-dependent summation order of a full `mean()`)."""
+    if exact or dtype == "bf16":
         return f32_mismatches(got, ref) == 0
     with np.errstate(all="ignore"):
         if not (np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.isfinite(got), np.isfinite(ref))):

@@ -63,12 +63,8 @@ def test_lowbit_weight_matches_reference_goldens(dtype):
         w_bits, lw = int(tag[1]), tag.endswith("_lw")
         o = qo.lowbit_weight(w, w_bits, lw, dtype)["w_eff"]
         ref = U.bits_to_f32(g[k], dtype)
-        if dtype == "bf16":
-            assert qo.count_mismatch(o, ref) == 0, k
-        else:  # fp32: the row mean's summation order is not a portable contract
-            with np.errstate(all="ignore"):
-                rel = np.abs(o - ref) / (np.abs(ref) + 1e-30)
-            assert np.nanmax(rel) < 2e-6, (k, np.nanmax(rel))
+        # per-row scales and this small layerwise tensor (7680 elements) are bit contracts in both dtypes
+        assert qo.count_mismatch(o, ref) == 0, k
 
 
 def test_code_ranges_and_dequant_identity():
@@ -201,6 +197,7 @@ def test_oracle_lowbit_edge_cases_match_live_reference(monkeypatch):
             lin.weight.copy_(w)
         lin(torch.zeros(1, cols, dtype=w.dtype))
         ref = qo.lowbit_weight(U.tensor_to_f32(w), bits, lw, dtype)["w_eff"]
-        assert U.lowbit_close(U.tensor_to_f32(captured["w"]), ref, dtype), (dtype, rows, cols, bits, lw)
+        assert U.lowbit_close(U.tensor_to_f32(captured["w"]), ref, dtype, U.lowbit_exact(lw, w.numel())), \
+            (dtype, rows, cols, bits, lw)
         n += 1
-    assert n == 40
+    assert n == 72
