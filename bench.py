@@ -367,8 +367,8 @@ def time_shape_sweep(device, steps, pk):
             out[f"bf16[{rows},{cols}] {mode}"] = {"fwd": {"us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
                                                          "frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)}}
         del cs, outs, gs, ms
-    # QuantizeLinear's W1 / W2 weight path (utils_quant.py:202-242): mean|w| per row, then apply, in one
-    # pass with the row in registers: 2e B/elem
+    # QuantizeLinear's W1 / W2 weight path (utils_quant.py:202-242): mean|w| per row (torch's summation order),
+    # then apply, in one pass with the row staged in shared memory: 2e B/elem
     for dt_name, dt, tdt, esz in (("bf16", 1, torch.bfloat16, 2), ("fp32", 0, torch.float32, 4)):
         rows, cols = 11008, 4096
         n = rows * cols

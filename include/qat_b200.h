@@ -131,6 +131,11 @@ int qat_ste_bwd_from_mask(const void* g, const uint8_t* mask, void* gx, int64_t 
  * QuantizeLinear low-bit weight path — utils_quant.py:202-242 (w_bits in {1,2}).
  * w_eff = fl(fl(q - w) + w) with q the 1-bit sign / 2-bit 4-level quantization
  * scaled by the row (or tensor) mean |w|.  rows = out_features.
+ * The row mean is summed in the order of torch's CPU reduction (csrc/torch_sum_order.cuh), so w_eff
+ * carries the reference's bits in fp32 and bf16 for any width and alignment (rows up to ~220 KB; one
+ * pass).  Layerwise: exact below 32768 elements; above, torch splits the reduction over its threads
+ * (no machine-independent result exists) and a double-precision sum is used — like for longer rows —
+ * through `workspace` (two passes).  w and w_eff must not alias.
  */
 size_t qat_lowbit_workspace_bytes(int64_t rows, int layerwise); /* 8 B per row, or 8 B layerwise */
 int qat_lowbit_weight_fwd(const void* w, void* w_eff, int64_t rows, int64_t cols, int dtype,
