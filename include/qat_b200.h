@@ -292,7 +292,9 @@ int qat_swiglu_bwd(const void* grad_act, const void* gate, const void* up, void*
  * models/modeling_llama_quant.py:320-341: key / value = SymQuantizer.apply(k_proj / v_proj output,
  * [-2, 2], kv_bits, False) per token over all heads' channels (skipped when kv_bits >= 32), then
  * apply_rotary_pos_emb on query and key (:174-196).  q, k, v and the outputs: bf16 [tokens, heads * 128];
- * cos_table / sin_table: fp32 [max_pos, 128] (LlamaRotaryEmbedding's caches); position_ids int64 [tokens].
+ * cos_table / sin_table: fp32 [max_pos, 128] (LlamaRotaryEmbedding's caches); position_ids int64 [tokens]:
+ * negative ids count from the end of the table like the reference's `cos[position_ids]`, ids >= max_pos (an
+ * IndexError there) are clamped to the last row — no launch reads outside the tables.
  * k_mask / v_mask receive the packed STE pass-masks of the unquantized K / V.  The fake-quantized values
  * are bit-identical to qat_sym_fwd's (same chain); under QAT_BF16_AMP K is rotated in fp32 and rounded
  * once to bf16, as autocast's matmul cast does.
@@ -300,12 +302,12 @@ int qat_swiglu_bwd(const void* grad_act, const void* gate, const void* up, void*
  */
 int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, void* q_out, void* k_out, void* v_out,
                      uint8_t* k_mask, uint8_t* v_mask, const float* cos_table, const float* sin_table,
-                     const int64_t* position_ids, int64_t tokens, int heads, int head_dim, int kv_bits,
-                     float clip_lo, float clip_hi, int dtype, void* stream);
+                     const int64_t* position_ids, int64_t max_pos, int64_t tokens, int heads, int head_dim,
+                     int kv_bits, float clip_lo, float clip_hi, int dtype, void* stream);
 int qat_qkv_prep_bwd(const void* dq_rot, const void* dk_rot, const void* dv_q, const uint8_t* k_mask,
                      const uint8_t* v_mask, const float* cos_table, const float* sin_table,
-                     const int64_t* position_ids, void* dq, void* dk, void* dv, int64_t tokens, int heads,
-                     int head_dim, void* stream);
+                     const int64_t* position_ids, int64_t max_pos, void* dq, void* dk, void* dv, int64_t tokens,
+                     int heads, int head_dim, void* stream);
 
 /* Host-buffer convenience entry points (pinned or pageable host memory):
  * copy in, run, copy out on `stream`; `dev_scratch` must hold

@@ -76,9 +76,9 @@ def _declare(lib):
         # g, gate, up, d_gate, d_up, n, stream
         "qat_swiglu_bwd": (I, [P, P, P, P, P, L, P]),
         # q, k, v, qo, ko, vo, kmask, vmask, cos, sin, pos, tokens, heads, head_dim, kv_bits, lo, hi, dtype, stream
-        "qat_qkv_prep_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, F, F, I, P]),
+        "qat_qkv_prep_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, L, I, I, I, F, F, I, P]),
         # dq_rot, dk_rot, dv_q, kmask, vmask, cos, sin, pos, dq, dk, dv, tokens, heads, head_dim, stream
-        "qat_qkv_prep_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, I, P]),
+        "qat_qkv_prep_bwd": (I, [P, P, P, P, P, P, P, P, L, P, P, P, L, I, I, P]),
         "qat_attn_debug_trace": (I, [P]),
         "qat_host_scratch_bytes": (Z, [L, L, I, I]),
         # x_host, g_host, y_host, gx_host, lo, hi, rows, cols, dtype, bits, scratch, scratch_bytes, stream

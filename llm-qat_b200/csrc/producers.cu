@@ -356,10 +356,18 @@ struct QkvParams {
   const float* cos;  // [max_pos, 128] fp32 tables (LlamaRotaryEmbedding.cos_cached / sin_cached)
   const float* sin;
   const int64_t* pos;  // [tokens] position ids
+  int64_t max_pos;     // rows of the tables
   int nvec;            // vectors per token row = H * 16
   int kv_bits;         // >= 32: no K/V fake-quant
   float lo, hi, qmax;
 };
+
+// table row of a position id: negative ids count from the end like the reference's `cos[position_ids]`
+// (torch indexing); ids past the table — an IndexError there — are clamped so that no launch reads out of bounds
+__device__ __forceinline__ int64_t rope_row(int64_t pos, int64_t max_pos) {
+  if (pos < 0) pos += max_pos;
+  return pos < 0 ? 0 : (pos >= max_pos ? max_pos - 1 : pos);
+}
 
 template <int DT, int kQkvIters>
 __global__ void __launch_bounds__(kThreads) qkv_prep_kernel(const QkvParams p) {
@@ -367,8 +375,9 @@ __global__ void __launch_bounds__(kThreads) qkv_prep_kernel(const QkvParams p) {
   pdl_wait();
   pdl_launch_dependents();
   const int64_t row = blockIdx.x;
-  const float* cs = p.cos + p.pos[row] * 128;
-  const float* sn = p.sin + p.pos[row] * 128;
+  const int64_t trow = rope_row(p.pos[row], p.max_pos);
+  const float* cs = p.cos + trow * 128;
+  const float* sn = p.sin + trow * 128;
   uint4 kv[kQkvIters], vv[kQkvIters];
   uint32_t kmax = 0u, vmax = 0u;
 #pragma unroll
@@ -446,13 +455,15 @@ __global__ void __launch_bounds__(kThreads) qkv_prep_bwd_kernel(const uint4* __r
                                                                 const uint8_t* __restrict__ v_mask,
                                                                 const float* __restrict__ cos_t,
                                                                 const float* __restrict__ sin_t,
-                                                                const int64_t* __restrict__ pos, uint4* __restrict__ dq,
-                                                                uint4* __restrict__ dk, uint4* __restrict__ dv, int nvec) {
+                                                                const int64_t* __restrict__ pos, int64_t max_pos,
+                                                                uint4* __restrict__ dq, uint4* __restrict__ dk,
+                                                                uint4* __restrict__ dv, int nvec) {
   pdl_wait();
   pdl_launch_dependents();
   const int64_t row = blockIdx.x;
-  const float* cs = cos_t + pos[row] * 128;
-  const float* sn = sin_t + pos[row] * 128;
+  const int64_t trow = rope_row(pos[row], max_pos);
+  const float* cs = cos_t + trow * 128;
+  const float* sn = sin_t + trow * 128;
 #pragma unroll 1
   for (int i = 0; i < kQkvIters; ++i) {
     const int j = threadIdx.x + i * kThreads;
@@ -643,8 +654,8 @@ extern "C" int qat_swiglu_bwd(const void* grad_act, const void* gate, const void
 
 extern "C" int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, void* q_out, void* k_out, void* v_out,
                                 uint8_t* k_mask, uint8_t* v_mask, const float* cos_table, const float* sin_table,
-                                const int64_t* position_ids, int64_t tokens, int heads, int head_dim, int kv_bits,
-                                float clip_lo, float clip_hi, int dtype, void* stream) {
+                                const int64_t* position_ids, int64_t max_pos, int64_t tokens, int heads, int head_dim,
+                                int kv_bits, float clip_lo, float clip_hi, int dtype, void* stream) {
   using namespace qat;
   QAT_CHECK_ARG(dtype == QAT_BF16 || dtype == QAT_BF16_AMP, "dtype must be QAT_BF16 or QAT_BF16_AMP (got %d)", dtype);
   QAT_CHECK_ARG(head_dim == 128, "head_dim must be 128 (got %d)", head_dim);
@@ -652,6 +663,7 @@ extern "C" int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, voi
   QAT_CHECK_ARG(kv_bits >= 2, "kv_bits must be >= 2 (got %d)", kv_bits);
   QAT_CHECK_ARG(tokens >= 0, "negative token count");
   if (tokens == 0) return QAT_OK;
+  QAT_CHECK_ARG(max_pos > 0, "max_pos (rows of the cos / sin tables) must be positive (got %lld)", (long long)max_pos);
   QAT_CHECK_ARG(q && k && v && q_out && k_out && v_out && cos_table && sin_table && position_ids, "NULL operand");
   QAT_CHECK_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)q_out | (uintptr_t)k_out | (uintptr_t)v_out) & 15) == 0,
                 "operands must be 16-byte aligned");
@@ -668,6 +680,7 @@ extern "C" int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, voi
   p.cos = cos_table;
   p.sin = sin_table;
   p.pos = position_ids;
+  p.max_pos = max_pos;
   p.nvec = heads * 16;
   p.kv_bits = kv_bits;
   p.lo = bf16_round_host(clip_lo);
@@ -689,12 +702,13 @@ extern "C" int qat_qkv_prep_fwd(const void* q, const void* k, const void* v, voi
 
 extern "C" int qat_qkv_prep_bwd(const void* dq_rot, const void* dk_rot, const void* dv_q, const uint8_t* k_mask,
                                 const uint8_t* v_mask, const float* cos_table, const float* sin_table,
-                                const int64_t* position_ids, void* dq, void* dk, void* dv, int64_t tokens, int heads,
-                                int head_dim, void* stream) {
+                                const int64_t* position_ids, int64_t max_pos, void* dq, void* dk, void* dv,
+                                int64_t tokens, int heads, int head_dim, void* stream) {
   using namespace qat;
   QAT_CHECK_ARG(head_dim == 128, "head_dim must be 128 (got %d)", head_dim);
   QAT_CHECK_ARG(heads > 0 && heads * 16 <= kThreads * kQkvMaxIters, "unsupported head count %d", heads);
   if (tokens <= 0) return QAT_OK;
+  QAT_CHECK_ARG(max_pos > 0, "max_pos (rows of the cos / sin tables) must be positive (got %lld)", (long long)max_pos);
   QAT_CHECK_ARG(dq_rot && dk_rot && dv_q && dq && dk && dv && cos_table && sin_table && position_ids, "NULL operand");
   QAT_CHECK_ARG((((uintptr_t)dq_rot | (uintptr_t)dk_rot | (uintptr_t)dv_q | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
                 "operands must be 16-byte aligned");
@@ -703,7 +717,8 @@ extern "C" int qat_qkv_prep_bwd(const void* dq_rot, const void* dk_rot, const vo
   QAT_DISPATCH_ITERS(iters_for(heads * 16), kQkvMaxIters,
                      e = launch_pdl(qkv_prep_bwd_kernel<I>, dim3((unsigned)tokens), dim3(kThreads), 0, st,
                                     (const uint4*)dq_rot, (const uint4*)dk_rot, (const uint4*)dv_q, k_mask, v_mask,
-                                    cos_table, sin_table, position_ids, (uint4*)dq, (uint4*)dk, (uint4*)dv, heads * 16));
+                                    cos_table, sin_table, position_ids, max_pos, (uint4*)dq, (uint4*)dk, (uint4*)dv,
+                                    heads * 16));
   if (e != cudaSuccess) return cuda_fail(e, "qkv_prep_bwd_kernel launch");
   QAT_CHECK_LAUNCH("qkv_prep_bwd_kernel");
   return QAT_OK;

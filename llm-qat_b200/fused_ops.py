@@ -272,13 +272,13 @@ class _QKVPrep(torch.autograd.Function):
         quant = kv_bits < 32
         km = torch.empty(T * hidden // 8 if quant else 0, dtype=torch.uint8, device=dev)
         vm = torch.empty_like(km)
-        pos = pos.reshape(-1).to(torch.int64).contiguous()
+        pos = pos.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
         with torch.cuda.device(dev):
             check(_lib.lib().qat_qkv_prep_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), qo.data_ptr(), ko.data_ptr(),
                                               vo.data_ptr(), km.data_ptr() if quant else 0,
                                               vm.data_ptr() if quant else 0, cos.data_ptr(), sin.data_ptr(),
-                                              pos.data_ptr(), T, heads, hidden // heads, int(kv_bits), lo, hi, dt,
-                                              _stream(dev)), "qat_qkv_prep_fwd")
+                                              pos.data_ptr(), cos.shape[0], T, heads, hidden // heads, int(kv_bits),
+                                              lo, hi, dt, _stream(dev)), "qat_qkv_prep_fwd")
         ctx.save_for_backward(km, vm, cos, sin, pos)
         ctx.meta = (T, heads, hidden // heads, quant)
         return qo, ko, vo
@@ -293,8 +293,8 @@ class _QKVPrep(torch.autograd.Function):
         with torch.cuda.device(a.device):
             check(_lib.lib().qat_qkv_prep_bwd(a.data_ptr(), b.data_ptr(), c.data_ptr(), km.data_ptr() if quant else 0,
                                               vm.data_ptr() if quant else 0, cos.data_ptr(), sin.data_ptr(),
-                                              pos.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), T, heads, hd,
-                                              _stream(a.device)), "qat_qkv_prep_bwd")
+                                              pos.data_ptr(), cos.shape[0], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                              T, heads, hd, _stream(a.device)), "qat_qkv_prep_bwd")
         return dq, dk, dv, None, None, None, None, None, None, None, None
 
 
@@ -306,6 +306,15 @@ def qkv_prep(q, k, v, cos_table, sin_table, position_ids, heads: int, kv_bits: i
         raise RuntimeError("qkv_prep: CUDA bfloat16 tensors required")
     if q.shape[-1] != heads * 128:
         raise RuntimeError("qkv_prep: head_dim must be 128")
+    if k.shape != q.shape or v.shape != q.shape:
+        raise RuntimeError(f"qkv_prep: q, k, v must have one shape, got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    for name, tab in (("cos_table", cos_table), ("sin_table", sin_table)):
+        if not (tab.is_cuda and tab.dtype == torch.float32 and tab.dim() == 2 and tab.shape[1] == 128 and tab.is_contiguous()):
+            raise RuntimeError(f"qkv_prep: {name} must be a contiguous CUDA float32 [max_pos, 128] tensor")
+    if cos_table.shape != sin_table.shape or cos_table.shape[0] == 0:
+        raise RuntimeError("qkv_prep: cos_table and sin_table must have one non-empty shape")
+    if position_ids.numel() != q.numel() // q.shape[-1]:
+        raise RuntimeError("qkv_prep: one position id per token expected")
     dt = _amp_dtype(k)
     return _QKVPrep.apply(q, k, v, cos_table, sin_table, position_ids, int(heads), int(kv_bits), float(clip[0]),
                           float(clip[1]), dt)

@@ -1030,6 +1030,45 @@ def test_qkv_prep_equals_kv_fake_quant_then_rope(amp, kv_bits):
     assert bool(((k1.grad == 0) == (k2.grad == 0)).float().mean() > 0.999)
 
 
+def test_qkv_prep_position_ids_outside_the_tables_stay_in_bounds():
+    """`cos[position_ids]` (modeling_llama_quant.py:189-190): negative ids count from the end of the table, like
+    torch indexing; ids past the table raise IndexError in the reference — here they are clamped to the last
+    row, so a bad id can never read outside the tables (forward and backward)."""
+    from harness import llama_qat as H
+    from llm_qat_b200.fused_ops import qkv_prep
+
+    S, nh, max_pos = 64, 2, 80
+    gen = torch.Generator().manual_seed(43)
+    mk = lambda: torch.randn(1, S, nh * 128, generator=gen).bfloat16().cuda()  # noqa: E731
+    q0, k0, v0, gq, gk, gv = mk(), mk(), mk(), mk(), mk(), mk()
+    rot = H.RotaryEmbedding(128, max_pos).cuda()
+    cos_t, sin_t = rot.cos_cached[0, 0].contiguous(), rot.sin_cached[0, 0].contiguous()
+    assert cos_t.shape[0] == max_pos
+
+    def run(pos):
+        q, k, v = (t.clone().requires_grad_(True) for t in (q0, k0, v0))
+        out = qkv_prep(q, k, v, cos_t, sin_t, pos, nh, 4)
+        torch.autograd.backward(out, (gq, gk, gv))
+        return [t.detach() for t in out] + [q.grad, k.grad, v.grad]
+
+    good = torch.arange(S, device="cuda")[None] + 10                      # 10 .. 73
+    wrapped = good - max_pos                                                # the same rows, counted from the end
+    for a, b in zip(run(good), run(wrapped)):
+        assert torch.equal(a, b)
+    wild = good.clone()
+    wild[0, ::3] = 10 ** 12
+    wild[0, 1::3] = -(10 ** 12)
+    clamped = good.clone()
+    clamped[0, ::3] = max_pos - 1
+    clamped[0, 1::3] = 0
+    for a, b in zip(run(wild), run(clamped)):
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        qkv_prep(q0, k0[:, :32], v0, cos_t, sin_t, good, nh, 4)
+    with pytest.raises(RuntimeError):
+        qkv_prep(q0, k0, v0, cos_t.double(), sin_t, good, nh, 4)
+
+
 @pytest.mark.parametrize("a_mn", [0, 1])
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("shape", [(256, 256, 128), (304, 528, 200), (2048, 1024, 1088)])
