@@ -7,9 +7,11 @@
 // a three-stage pipeline — H2D(x, g) | K1/K2 + K3 | D2H(y, gx) — overlapping
 // both PCIe directions with the kernels.  One stream per direction: measured on
 // the B200 box, two concurrent copies in the SAME direction (x beside g) drop the
-// link from 41 to 33 GB/s per direction, so kStreamsPerDirection stays 1.  The
+// link from 41 to 33 GB/s per direction.  The
 // ceiling is the link itself: 47 GB/s per direction with both directions busy
-// (tests/gpu_pcie_probe.py), 41 GB/s at this pipeline's 8 MB copy size.  Everything is ordered
+// (tests/gpu_pcie_probe.py); this pipeline sustains 42 (tests/gpu_e2e_probe.py, profiles/r02_e2e_sweep.json:
+// 7.75 ms per configs[1] step with round 1's schedule at 8 MB, 7.50 ms with the split schedule at 16 MB).
+// Everything is ordered
 // after prior work on the caller's stream and the caller's stream waits for the
 // last D2H, so stream semantics are those of a single asynchronous call.
 #define QAT_PDL_FAMILY 9   // bit of QAT_B200_PDL_MASK (common.cuh)
@@ -22,7 +24,7 @@ namespace qat {
 namespace {
 
 struct Pipe {
-  cudaStream_t in[2] = {nullptr, nullptr}, out[2] = {nullptr, nullptr};
+  cudaStream_t in = nullptr, out = nullptr;   // one stream per PCIe direction
   std::vector<cudaEvent_t> ev;
   int device = -1;
   cudaEvent_t event(size_t i) {
@@ -45,10 +47,8 @@ Pipe* get_pipe() {
     if (p.device == dev) return &p;
   Pipe p;
   p.device = dev;
-  for (int i = 0; i < 2; ++i) {
-    if (cudaStreamCreateWithFlags(&p.in[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&p.out[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-  }
+  if (cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
   pipes.push_back(p);
   return &pipes.back();
 }
@@ -58,7 +58,7 @@ int64_t target_chunk_bytes() {
   static const int64_t v = [] {
     const char* e = getenv("QAT_B200_HOST_CHUNK_MB");
     const int mb = e ? atoi(e) : 0;
-    return (int64_t)((mb >= 1 && mb <= 64) ? mb : 8) << 20;
+    return (int64_t)((mb >= 1 && mb <= 64) ? mb : 16) << 20;
   }();
   return v;
 }
@@ -96,7 +96,7 @@ int fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_
   char* dg = dy + tensor_bytes;
   char* dgx = dg + tensor_bytes;
 
-  // Chunk schedule: steady-state chunks of ~8 MB per tensor (smaller ones are
+  // Chunk schedule: steady-state chunks of ~16 MB per tensor (smaller ones are
   // bound by the host's enqueue rate), but the first and last chunks ramp
   // 1/8, 1/4, 1/2 of that: the D2H direction idles while the first chunk goes
   // in, and the H2D direction while the last one comes out, so short end
@@ -135,51 +135,67 @@ int fwd_bwd_host(const void* x_host, const void* g_host, void* y_host, void* gx_
     if (e != cudaSuccess) return cuda_fail(e, #call);  \
   } while (0)
 
-  const int lanes = bwd ? 2 : 1;  // lane 0: x -> y, lane 1: g -> gx
-  constexpr int kStreamsPerDirection = 1;
   cudaEvent_t ev_start = pipe->event(0);
   if (ev_start == nullptr) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
   QAT_TRY(cudaEventRecord(ev_start, st));
-  for (int l = 0; l < lanes; ++l) {
-    QAT_TRY(cudaStreamWaitEvent(pipe->in[l % kStreamsPerDirection], ev_start, 0));
-    QAT_TRY(cudaStreamWaitEvent(pipe->out[l % kStreamsPerDirection], ev_start, 0));
-  }
+  QAT_TRY(cudaStreamWaitEvent(pipe->in, ev_start, 0));
+  QAT_TRY(cudaStreamWaitEvent(pipe->out, ev_start, 0));
 
+  // Within a chunk the forward needs x only: x goes in, K1/K2 runs and y starts its way back while g is still
+  // going in; then K3 and gx.  The outbound direction so trails the inbound one by HALF a chunk (one tensor's
+  // slice), which lets the copies be twice as long for the same pipeline granularity.
+  // QAT_B200_HOST_SCHEDULE=chunk: both inputs first, then both kernels, then both outputs (round 1's order).
+  static const bool split = [] {
+    const char* e = getenv("QAT_B200_HOST_SCHEDULE");
+    return !(e && e[0] == 'c');
+  }();
+  cudaStream_t s_in = pipe->in, s_out = pipe->out;
+  const char* src[2] = {reinterpret_cast<const char*>(x_host), reinterpret_cast<const char*>(g_host)};
+  char* dst_dev[2] = {dx, dg};
+  const char* src_dev[2] = {dy, dgx};
+  char* dst[2] = {reinterpret_cast<char*>(y_host), reinterpret_cast<char*>(gx_host)};
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t r0 = bounds[c];
     const int64_t nr = bounds[c + 1] - r0;
     const int64_t off = r0 * row_bytes, bytes = nr * row_bytes;
-    cudaEvent_t ev_in[2] = {pipe->event(1 + 3 * c), pipe->event(2 + 3 * c)}, ev_k = pipe->event(3 + 3 * c);
-    if (ev_in[0] == nullptr || ev_in[1] == nullptr || ev_k == nullptr)
+    cudaEvent_t ev_in[2] = {pipe->event(1 + 4 * c), pipe->event(2 + 4 * c)};
+    cudaEvent_t ev_k[2] = {pipe->event(3 + 4 * c), pipe->event(4 + 4 * c)};
+    if (ev_in[0] == nullptr || ev_in[1] == nullptr || ev_k[0] == nullptr || ev_k[1] == nullptr)
       return cuda_fail(cudaGetLastError(), "cudaEventCreate");
-    const char* src[2] = {reinterpret_cast<const char*>(x_host), reinterpret_cast<const char*>(g_host)};
-    char* dst_dev[2] = {dx, dg};
-    for (int l = 0; l < lanes; ++l) {
-      QAT_TRY(cudaMemcpyAsync(dst_dev[l] + off, src[l] + off, bytes, cudaMemcpyHostToDevice, pipe->in[l % kStreamsPerDirection]));
-      QAT_TRY(cudaEventRecord(ev_in[l], pipe->in[l % kStreamsPerDirection]));
-      QAT_TRY(cudaStreamWaitEvent(st, ev_in[l], 0));
-    }
-    int rc = SYM ? qat_sym_fwd(dx + off, dy + off, nullptr, QAT_CODES_NONE, nullptr, nullptr, nullptr,
-                               lo, hi, nr, cols, dtype, bits, nullptr, 0, st)
-                 : qat_asym_fwd(dx + off, dy + off, nullptr, QAT_CODES_NONE, nullptr, nullptr, nullptr,
-                                lo, hi, nr, cols, dtype, bits, nullptr, 0, st);
-    if (rc != QAT_OK) return rc;
+    auto copy_in = [&](int l) -> cudaError_t {
+      cudaError_t ce = cudaMemcpyAsync(dst_dev[l] + off, src[l] + off, bytes, cudaMemcpyHostToDevice, s_in);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ev_in[l], s_in);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, ev_in[l], 0);
+      return ce;
+    };
+    auto copy_out = [&](int l) -> cudaError_t {   // after the kernel(s) enqueued on st so far
+      cudaError_t ce = cudaEventRecord(ev_k[l], st);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s_out, ev_k[l], 0);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst[l] + off, src_dev[l] + off, bytes, cudaMemcpyDeviceToHost, s_out);
+      return ce;
+    };
+    auto forward = [&]() -> int {
+      return SYM ? qat_sym_fwd(dx + off, dy + off, nullptr, QAT_CODES_NONE, nullptr, nullptr, nullptr, lo, hi, nr, cols,
+                               dtype, bits, nullptr, 0, st)
+                 : qat_asym_fwd(dx + off, dy + off, nullptr, QAT_CODES_NONE, nullptr, nullptr, nullptr, lo, hi, nr, cols,
+                                dtype, bits, nullptr, 0, st);
+    };
+    int rc;
+    QAT_TRY(copy_in(0));
+    if (bwd && !split) QAT_TRY(copy_in(1));
+    if ((rc = forward()) != QAT_OK) return rc;
+    if (!bwd || split) QAT_TRY(copy_out(0));
     if (bwd) {
-      rc = qat_ste_bwd(dg + off, dx + off, dgx + off, nullptr, lo, hi, nr * cols, dtype, st);
-      if (rc != QAT_OK) return rc;
-    }
-    QAT_TRY(cudaEventRecord(ev_k, st));
-    const char* src_dev[2] = {dy, dgx};
-    char* dst[2] = {reinterpret_cast<char*>(y_host), reinterpret_cast<char*>(gx_host)};
-    for (int l = 0; l < lanes; ++l) {
-      QAT_TRY(cudaStreamWaitEvent(pipe->out[l % kStreamsPerDirection], ev_k, 0));
-      QAT_TRY(cudaMemcpyAsync(dst[l] + off, src_dev[l] + off, bytes, cudaMemcpyDeviceToHost, pipe->out[l % kStreamsPerDirection]));
+      if (split) QAT_TRY(copy_in(1));
+      if ((rc = qat_ste_bwd(dg + off, dx + off, dgx + off, nullptr, lo, hi, nr * cols, dtype, st)) != QAT_OK) return rc;
+      if (!split) QAT_TRY(copy_out(0));
+      QAT_TRY(copy_out(1));
     }
   }
-  for (int l = 0; l < lanes; ++l) {
-    cudaEvent_t ev_done = pipe->event(1 + 3 * nchunks + l);
+  {
+    cudaEvent_t ev_done = pipe->event(1 + 4 * nchunks);
     if (ev_done == nullptr) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
-    QAT_TRY(cudaEventRecord(ev_done, pipe->out[l % kStreamsPerDirection]));
+    QAT_TRY(cudaEventRecord(ev_done, s_out));
     QAT_TRY(cudaStreamWaitEvent(st, ev_done, 0));
   }
 #undef QAT_TRY
