@@ -64,6 +64,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
 
 // Debug hook (tests/gpu_attn_trace.py): when set, CTA (0,0,0) of attn_fwd_kernel records clock64() at its
 // phase boundaries — slots [role][tile][event] of a device buffer — so the per-tile critical path can be
@@ -82,6 +85,7 @@ struct AttnParams {
   int B, S, H;
   float scale;         // 1 / sqrt(D)
   int causal;
+  int pingpong;        // fwd: the two softmax warpgroups take turns at the exponentials (QAT_B200_ATTN_PINGPONG, default 1)
 };
 
 // =============================================================================================
@@ -244,6 +248,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float l_run = 0.f;
     int uses = 0;
     const bool tr = (threadIdx.x == 64 || threadIdx.x == 192);
+    // exp token: warpgroup 0 goes first (warpgroup 1 hands it the token up front); the turns alternate strictly
+    // — tile 0, 1, 2, ... — which is also the order the S tiles are produced in
+    const bool pingpong = p.pingpong != 0 && n_kv > 1;
+    if (pingpong && wg == 1) named_bar_arrive(2, 256);
     for (int j = wg; j < n_kv; j += 2, ++uses) {
       const uint32_t ph = (uint32_t)(uses & 1);
       if (tr) trace(1 + wg, j, 0);
@@ -262,19 +270,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (tr) trace(1 + wg, j, 2);
       const int k0 = j * BM;
       const bool edge = (p.causal && k0 + BM - 1 > q0) || (k0 + BM > p.S);
-      float mx = -INFINITY;
       if (edge) {
 #pragma unroll
         for (int i = 0; i < 128; ++i) {
           const int k_idx = k0 + i;
           const bool dead = k_idx >= p.S || (p.causal && k_idx > q_idx);
           if (dead) sv[i] = 0xff800000u;   // -inf
-          mx = fmaxf(mx, __uint_as_float(sv[i]));
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four chains: 32 dependent max ops, not 128
+#pragma unroll
+      for (int i = 0; i < 128; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^8 in the
       // exponent (p <= 256 stays exact enough in bf16 and far from fp32 overflow)
       if (tr) trace(1 + wg, j, 3);
@@ -283,16 +290,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float m_use = grow ? m_new : m_run;
       const float alpha = grow ? ex2f((m_run - m_use) * c) : 1.0f;   // first tile: ex2(-inf) = 0
       const float mc = m_use * c;
-      float sum = 0.f;
+      // The exponentials are what bounds a tile (16384 ex2 at the SM's 16 per clock = 1024 cycles): the two
+      // warpgroups take turns at them (named barriers 2 / 3 as a token), so that one warpgroup's TMEM loads,
+      // row max, P stores and barrier waits run under the other's exponentials instead of both halving each
+      // other's MUFU rate and then both leaving the unit idle (tests/gpu_attn_trace.py).
+      if (pingpong) named_bar_sync(2 + wg, 256);
+      float sum2[2] = {0.f, 0.f};
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 128; i += 2) {
         const float p0 = ex2f(fmaf(__uint_as_float(sv[i]), c, -mc));
         const float p1 = ex2f(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
-        sum += p0 + p1;
+        sum2[(i >> 1) & 1] += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
-      l_run = l_run * alpha + sum;
+      if (pingpong) named_bar_arrive(3 - wg, 256);
+      l_run = l_run * alpha + (sum2[0] + sum2[1]);
       m_run = m_use;
       if (tr) trace(1 + wg, j, 4);
       if (uses > 0) {
@@ -936,6 +949,11 @@ extern "C" int qat_attn_fwd(const void* q, const void* k, const void* v, void* o
   p.H = H;
   p.scale = softmax_scale;
   p.causal = causal ? 1 : 0;
+  static const int pingpong = [] {
+    const char* e = getenv("QAT_B200_ATTN_PINGPONG");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  p.pingpong = pingpong;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const dim3 grid((unsigned)((S + BM - 1) / BM), (unsigned)H, (unsigned)B);
   cudaError_t e = launch_pdl(attn_fwd_kernel, grid, dim3(fwd::kThreads), fwd::kSmem, st, mq, mk, mv, p);
