@@ -16,6 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import check
+from .utils_quant import _on     # device guard that is free when the device is already current
 
 
 def _stream(dev) -> int:
@@ -31,7 +32,7 @@ class _CausalAttention(torch.autograd.Function):
         q, k, v = (t if t.is_contiguous() else t.contiguous() for t in (q.detach(), k.detach(), v.detach()))
         o = torch.empty_like(q)
         lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             check(_lib.lib().qat_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
                                           B, S, H, D, float(scale), int(causal), _stream(q.device)), "qat_attn_fwd")
         ctx.save_for_backward(q, k, v, o, lse)
@@ -47,7 +48,7 @@ class _CausalAttention(torch.autograd.Function):
             d_o = d_o.contiguous()
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         delta = torch.empty_like(lse)
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             check(_lib.lib().qat_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
                                           lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(),
                                           dv.data_ptr(), B, S, H, D, ctx.scale, ctx.causal, _stream(q.device)),
@@ -91,7 +92,7 @@ class _KDLoss(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         row_kl = torch.empty(B * S, dtype=torch.float32, device=dev)
         row_stat = torch.empty(B * S * 4, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(_lib.lib().qat_kd_loss_fwd(s.data_ptr(), t.data_ptr(), loss.data_ptr(), row_kl.data_ptr(),
                                              row_stat.data_ptr(), B * S, V, B, dt, _stream(dev)), "qat_kd_loss_fwd")
         ctx.save_for_backward(s, t, row_stat)
@@ -104,7 +105,7 @@ class _KDLoss(torch.autograd.Function):
         B, S, V, dt = ctx.dims
         g = grad_loss.detach().to(device=s.device, dtype=torch.float32).contiguous()
         gs = torch.empty_like(s)
-        with torch.cuda.device(s.device):
+        with _on(s.device):
             check(_lib.lib().qat_kd_loss_bwd(s.data_ptr(), t.data_ptr(), row_stat.data_ptr(), g.data_ptr(),
                                              gs.data_ptr(), B * S, V, B, dt, _stream(s.device)), "qat_kd_loss_bwd")
         return gs, None
@@ -158,7 +159,7 @@ class _RMSNormFeed(torch.autograd.Function):
         rstd = torch.empty(T, dtype=torch.float32, device=dev)
         blob = _new_blob(T, C, dev) if bits else torch.empty(0, dtype=torch.uint8, device=dev)
         c, e, m = _feed_ptrs(blob, T, C) if bits else (0, 0, 0)
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(_lib.lib().qat_rmsnorm_feed_fwd(xc.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr(), c, e, m,
                                                   -2.0, 2.0, T, C, float(eps), dt, int(bits) if bits else 8,
                                                   _stream(dev)), "qat_rmsnorm_feed_fwd")
@@ -178,7 +179,7 @@ class _RMSNormFeed(torch.autograd.Function):
         L = _lib.lib()
         nb = int(L.qat_rmsnorm_bwd_workspace_bytes(T, C))
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             check(L.qat_rmsnorm_bwd(g.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), gx.data_ptr(),
                                     gw.data_ptr(), ws.data_ptr(), nb, T, C, _stream(x.device)), "qat_rmsnorm_bwd")
         return gx, gw, None, None, None
@@ -225,7 +226,7 @@ class _SwiGLUFeed(torch.autograd.Function):
         act = torch.empty_like(g)
         blob = _new_blob(T, C, dev) if bits else torch.empty(0, dtype=torch.uint8, device=dev)
         c, e, m = _feed_ptrs(blob, T, C) if bits else (0, 0, 0)
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(_lib.lib().qat_swiglu_feed_fwd(g.data_ptr(), u.data_ptr(), act.data_ptr(), c, e, m, -2.0, 2.0, T, C,
                                                  dt, int(bits) if bits else 8, _stream(dev)), "qat_swiglu_feed_fwd")
         ctx.save_for_backward(g, u)
@@ -238,7 +239,7 @@ class _SwiGLUFeed(torch.autograd.Function):
         ga = gact.to(torch.bfloat16)
         ga = ga if ga.is_contiguous() else ga.contiguous()
         dg, du = torch.empty_like(g), torch.empty_like(u)
-        with torch.cuda.device(g.device):
+        with _on(g.device):
             check(_lib.lib().qat_swiglu_bwd(ga.data_ptr(), g.data_ptr(), u.data_ptr(), dg.data_ptr(), du.data_ptr(),
                                             g.numel(), _stream(g.device)), "qat_swiglu_bwd")
         return dg, du, None, None
@@ -273,7 +274,7 @@ class _QKVPrep(torch.autograd.Function):
         km = torch.empty(T * hidden // 8 if quant else 0, dtype=torch.uint8, device=dev)
         vm = torch.empty_like(km)
         pos = pos.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
-        with torch.cuda.device(dev):
+        with _on(dev):
             check(_lib.lib().qat_qkv_prep_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), qo.data_ptr(), ko.data_ptr(),
                                               vo.data_ptr(), km.data_ptr() if quant else 0,
                                               vm.data_ptr() if quant else 0, cos.data_ptr(), sin.data_ptr(),
@@ -290,7 +291,7 @@ class _QKVPrep(torch.autograd.Function):
         a, b, c = (t.to(torch.bfloat16) for t in (dq_rot, dk_rot, dv_q))
         a, b, c = (t if t.is_contiguous() else t.contiguous() for t in (a, b, c))
         dq, dk, dv = torch.empty_like(a), torch.empty_like(b), torch.empty_like(c)
-        with torch.cuda.device(a.device):
+        with _on(a.device):
             check(_lib.lib().qat_qkv_prep_bwd(a.data_ptr(), b.data_ptr(), c.data_ptr(), km.data_ptr() if quant else 0,
                                               vm.data_ptr() if quant else 0, cos.data_ptr(), sin.data_ptr(),
                                               pos.data_ptr(), cos.shape[0], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),

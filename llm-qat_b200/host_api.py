@@ -14,11 +14,14 @@ from .utils_quant import _DTYPES, _clip_bounds, _reduction_view, _stream_ptr
 _scratch = {}
 
 
-def _device_scratch(nbytes: int, device) -> torch.Tensor:
-    key = (torch.device(device).index or 0)
+def _device_scratch(nbytes: int, dev: torch.device, stream: int) -> torch.Tensor:
+    """Staging memory of the pipeline, kept per (device, stream): calls on one stream are ordered, so they
+    can share it; a call on another stream (or another device — "cuda" means the CURRENT one) gets its own."""
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (index, stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", index))
         _scratch[key] = buf
     return buf
 
@@ -50,11 +53,12 @@ def fake_quant_fwd_bwd_host(x: torch.Tensor, g: torch.Tensor | None, clip_val, n
     L = _lib.lib()
     dev = torch.device(device)
     nbytes = int(L.qat_host_scratch_bytes(rows, cols, dt, 1 if g is not None else 0))
-    scratch = _device_scratch(nbytes, dev)
+    stream = _stream_ptr(dev)
+    scratch = _device_scratch(nbytes, dev, stream)
     fn = L.qat_sym_fwd_bwd_host if symmetric else L.qat_asym_fwd_bwd_host
-    with torch.cuda.device(dev):
+    with torch.cuda.device(scratch.device):
         rc = fn(x.data_ptr(), g.data_ptr() if g is not None else 0, y.data_ptr(),
                 gx.data_ptr() if gx is not None else 0, lo, hi, rows, cols, dt, int(num_bits),
-                scratch.data_ptr(), scratch.numel(), _stream_ptr(dev))
+                scratch.data_ptr(), scratch.numel(), stream)
     _lib.check(rc, "qat_fwd_bwd_host")
     return y, gx

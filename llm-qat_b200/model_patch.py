@@ -22,6 +22,7 @@ model file, its classes, parameters and state dict are untouched and ``unfuse_mo
 """
 from __future__ import annotations
 
+import collections
 import types
 
 import torch
@@ -31,22 +32,33 @@ from .utils_quant import QuantizeLinear, SymQuantizer, _clip_bounds
 
 __all__ = ["fuse_model", "unfuse_model", "fuse_kd_loss", "mark_causal_mask"]
 
-# The additive causal mask most recently built by a fused model (strong reference: its storage cannot be
-# recycled while it is registered).  Attention treats a mask as causal iff it IS this storage.
-_CAUSAL = {"mask": None}
+# The additive causal masks most recently built by fused models (strong references: a registered mask's
+# storage cannot be recycled for another tensor).  Attention treats a mask as causal iff it IS one of these
+# storages.  More than one is kept because a step holds more than one model's mask at a time — the FP
+# teacher's and the student's (kd_trainer.py:53-64), whose checkpoint recompute presents the student's mask
+# again during backward — and the recompute must take the same path as the forward it repeats, whatever
+# the order of the two forwards.  [b, 1, s, s] bf16 at s = 2048 is 8 MB per entry.
+_CAUSAL_KEEP = 4
+_CAUSAL: collections.deque = collections.deque(maxlen=_CAUSAL_KEEP)
 
 
 def mark_causal_mask(mask: torch.Tensor) -> torch.Tensor:
     """Declare ``mask`` ([b, 1, s, s] additive, finfo.min above the diagonal, 0 elsewhere — what
     ``_make_causal_mask`` builds, modeling_llama_quant.py:60-92) as purely causal."""
-    _CAUSAL["mask"] = mask
+    if not _is_causal(mask):
+        _CAUSAL.append(mask)
     return mask
 
 
 def _is_causal(mask) -> bool:
-    ref = _CAUSAL["mask"]
-    return (mask is not None and ref is not None and mask.data_ptr() == ref.data_ptr() and mask.shape == ref.shape
-            and mask.dtype == ref.dtype and mask.device == ref.device)
+    if mask is None:
+        return False
+    ptr = mask.data_ptr()
+    for ref in tuple(_CAUSAL):      # a snapshot: autograd's backward thread may look while a forward registers
+        if (ptr == ref.data_ptr() and mask.shape == ref.shape and mask.dtype == ref.dtype
+                and mask.device == ref.device):
+            return True
+    return False
 
 
 def _fusable_linear(lin) -> int:
@@ -98,6 +110,11 @@ def _attention_forward(self, hidden_states, attention_mask=None, position_ids=No
     if (past_key_value is not None or output_attentions or position_ids is None or self.head_dim != 128
             or not _on_gpu(hidden_states) or not _is_causal(attention_mask)):
         return orig(hidden_states, attention_mask, position_ids, past_key_value, output_attentions, use_cache)
+    # the projections return the autocast dtype inside torch.autocast, else their input's: decide BEFORE running
+    # them, so that a model in another dtype (fp32, fp16) does not compute q/k/v twice
+    proj_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else hidden_states.dtype
+    if proj_dtype != torch.bfloat16:
+        return orig(hidden_states, attention_mask, position_ids, past_key_value, output_attentions, use_cache)
     bsz, q_len, _ = hidden_states.size()
     cos, sin = _rope_tables(self, q_len, hidden_states.device)
     if cos is None:
@@ -106,7 +123,8 @@ def _attention_forward(self, hidden_states, attention_mask=None, position_ids=No
     k = self.k_proj(hidden_states)
     v = self.v_proj(hidden_states)
     if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
-        # not the recipe's dtype: finish on the reference path from the projections we already have
+        # not reached with the reference's modules (see above); a foreign projection class that returns another
+        # dtype: take the reference path (it recomputes the projections)
         return orig(hidden_states, attention_mask, position_ids, past_key_value, output_attentions, use_cache)
     pos = position_ids.expand(bsz, q_len) if position_ids.shape[0] != bsz else position_ids
     kv_bits = int(getattr(self, "kv_bits", 32))     # a stock (teacher) LlamaAttention has no K/V fake-quant
@@ -151,9 +169,7 @@ def _prepare_mask(self, attention_mask, input_shape, inputs_embeds, past_key_val
     m = self._qat_orig_prepare(attention_mask, input_shape, inputs_embeds, past_key_values_length)
     if getattr(self, "_qat_plain_causal", False) and past_key_values_length == 0 and m is not None:
         mark_causal_mask(m)
-    else:
-        _CAUSAL["mask"] = None
-    return m
+    return m     # a padded / cached-prefix mask is simply never registered: its calls run the reference's attention
 
 
 def _bind(mod, name, fn):

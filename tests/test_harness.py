@@ -347,7 +347,14 @@ assert not MP._is_causal(m.clone())
 # ... a padded one is not
 model.model._qat_plain_causal = False
 m2 = model.model._prepare_decoder_attention_mask(torch.tensor([[0, 1, 1, 1, 1, 1, 1, 1]]).bool(), (1, 8), emb, 0)
-assert not MP._is_causal(m2) and not MP._is_causal(m)
+assert not MP._is_causal(m2) and MP._is_causal(m)     # m stays registered: it IS a causal mask and is kept alive
+# several models' masks are live in one step (teacher, then student, then the student's recompute in backward)
+m3 = MP.mark_causal_mask(torch.zeros(1, 1, 8, 8))
+assert MP._is_causal(m) and MP._is_causal(m3) and len(MP._CAUSAL) == 2
+MP.mark_causal_mask(m3); assert len(MP._CAUSAL) == 2              # re-registering is a no-op
+for _ in range(MP._CAUSAL_KEEP):                                   # bounded: the oldest entries fall out
+    MP.mark_causal_mask(torch.zeros(1, 1, 8, 8))
+assert not MP._is_causal(m) and len(MP._CAUSAL) == MP._CAUSAL_KEEP
 # a CPU call falls through to the reference's own forward code path selection (non-CUDA -> original)
 assert lay.self_attn._qat_orig_forward.__func__ is cls_fwd
 llm_qat_b200.unfuse_model(model)
