@@ -239,7 +239,7 @@ extern "C" int qat_kd_loss_bwd(const void* student, const void* teacher, const f
   using namespace qat;
   QAT_CHECK_ARG(dtype == QAT_F32 || dtype == QAT_BF16, "dtype must be QAT_F32 or QAT_BF16 (got %d)", dtype);
   QAT_CHECK_ARG(rows > 0 && V > 0 && batch > 0, "bad shape");
-  QAT_CHECK_ARG(student && teacher && row_stat && grad_student, "NULL operand");
+  QAT_CHECK_ARG(student && teacher && row_stat && grad_loss && grad_student, "NULL operand");
   QAT_CHECK_ARG(rows < (1ll << 31), "too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int vec_ok = rows_vec_ok(student, teacher, grad_student, V, dtype) ? 1 : 0;
